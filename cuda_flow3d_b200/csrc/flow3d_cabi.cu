@@ -1,0 +1,609 @@
+// flow3d_cabi.cu -- the C ABI (include/flow3d_c.h): argument checking, the stage wrappers and the
+// solver object that runs the coarse-to-fine loop of OpticalFlowE::ComputeFlow
+// (reference: src/optical_flow/optical_flow_e.cpp:132-601) on compact per-level device buffers.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "common.cuh"
+
+namespace f3d {
+
+static thread_local std::string g_last_error;
+static std::atomic<uint64_t> g_launches{0};
+
+void note_cuda_error(cudaError_t e, const char* what) {
+  g_last_error = std::string(what ? what : "cuda") + ": " + cudaGetErrorName(e) + " (" +
+                 cudaGetErrorString(e) + ")";
+}
+void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    note_cuda_error(e, what);
+    return FLOW3D_ERR_CUDA;
+  }
+  return FLOW3D_OK;
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      cached = 148;
+  }
+  return cached;
+}
+
+#define F3D_CUDA(call)                                   \
+  do {                                                   \
+    cudaError_t e_ = (call);                             \
+    if (e_ != cudaSuccess) {                             \
+      f3d::note_cuda_error(e_, #call);                   \
+      return e_ == cudaErrorMemoryAllocation ? FLOW3D_ERR_OUT_OF_MEMORY : FLOW3D_ERR_CUDA; \
+    }                                                    \
+  } while (0)
+
+#define F3D_TRY(expr)                  \
+  do {                                 \
+    int rc_ = (expr);                  \
+    if (rc_ != FLOW3D_OK) return rc_;  \
+  } while (0)
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Gaussian taps exactly as cuda_operation_convolution.cpp:85-108 (precision 3, pixel size 1.0):
+// double-precision evaluation, float storage, float running sum, float division.
+static int gauss_taps(float sigma, float* taps, int max_radius) {
+  const size_t precision = 3;
+  const float pixel_size = 1.0f;
+  const size_t radius = (size_t)(precision * sigma / pixel_size);
+  if ((int)radius > max_radius) return -1;
+  const int r = (int)radius;
+  for (int i = -r; i <= r; i++) {
+    float val = 1.0 / (sigma * std::sqrt(2.0 * 3.1415926)) *
+                std::exp(-(i * i * pixel_size * pixel_size) / (2.0 * sigma * sigma));
+    taps[i + r] = val;
+  }
+  float sum = 0.0;
+  for (int i = 0; i < 2 * r + 1; i++) sum = sum + taps[i];
+  for (int i = 0; i < 2 * r + 1; i++) taps[i] = taps[i] / sum;
+  return r;
+}
+
+static int gauss_blur(const float* in, float* out, float* tmp, Dims g, float sigma, cudaStream_t st) {
+  float taps[65];
+  const int r = gauss_taps(sigma, taps, 32);
+  if (r < 0) return FLOW3D_ERR_UNSUPPORTED;
+  F3D_TRY(launch_conv_axis(in, out, g, taps, r, 0, st));   // rows    (cuda_operation_convolution.cpp:170)
+  F3D_TRY(launch_conv_axis(out, tmp, g, taps, r, 1, st));  // columns (:174)
+  F3D_TRY(launch_conv_axis(tmp, out, g, taps, r, 2, st));  // slices  (:178)
+  return FLOW3D_OK;
+}
+
+static inline size_t aligned_ld(size_t w) { return (w + 3) & ~(size_t)3; }
+
+// X -> Y -> Z (cuda_operation_resample.cpp:95-105) through two scratch volumes
+static int resample(const float* in, const size_t id[3], size_t in_ld, float* out, const size_t od[3],
+                    size_t out_ld, float* ta, float* tb, cudaStream_t st) {
+  size_t d0[3] = {id[0], id[1], id[2]};
+  size_t d1[3] = {od[0], id[1], id[2]};
+  size_t d2[3] = {od[0], od[1], id[2]};
+  const size_t l1 = aligned_ld(od[0]);
+  F3D_TRY(launch_resample_axis(in, make_dims(d0, in_ld), ta, make_dims(d1, l1), 0, st));
+  F3D_TRY(launch_resample_axis(ta, make_dims(d1, l1), tb, make_dims(d2, l1), 1, st));
+  F3D_TRY(launch_resample_axis(tb, make_dims(d2, l1), out, make_dims(od, out_ld), 2, st));
+  return FLOW3D_OK;
+}
+
+static int solve_level(const float* fx, const float* fy, const float* fz, const float* ft,
+                       const float* u, const float* v, const float* w, float* du, float* dv,
+                       float* dw, float* phi, float* ksi, float* tdu, float* tdv, float* tdw, Dims g,
+                       const float h[3], size_t outer, size_t inner, float alpha, float eps_s,
+                       float eps_d, cudaStream_t st) {
+  const size_t bytes = (size_t)g.ps * g.d * sizeof(float);
+  // cuda_operation_solve.cpp:183-188
+  F3D_CUDA(cudaMemsetAsync(du, 0, bytes, st));
+  F3D_CUDA(cudaMemsetAsync(dv, 0, bytes, st));
+  F3D_CUDA(cudaMemsetAsync(dw, 0, bytes, st));
+  float *a0 = du, *a1 = dv, *a2 = dw, *b0 = tdu, *b1 = tdv, *b2 = tdw;
+  for (size_t i = 0; i < outer; ++i) {  // :194-257
+    F3D_TRY(launch_phi_ksi(fx, fy, fz, ft, u, v, w, a0, a1, a2, g, h[0], h[1], h[2], eps_s, eps_d, phi,
+                           ksi, st));
+    for (size_t j = 0; j < inner; ++j) {
+      F3D_TRY(launch_sweep(fx, fy, fz, ft, u, v, w, a0, a1, a2, phi, ksi, g, h[0], h[1], h[2], alpha,
+                           b0, b1, b2, st));
+      std::swap(a0, b0);
+      std::swap(a1, b1);
+      std::swap(a2, b2);
+    }
+  }
+  if (a0 != du) {  // odd number of sweeps: bring the iterate home
+    F3D_CUDA(cudaMemcpyAsync(du, a0, bytes, cudaMemcpyDeviceToDevice, st));
+    F3D_CUDA(cudaMemcpyAsync(dv, a1, bytes, cudaMemcpyDeviceToDevice, st));
+    F3D_CUDA(cudaMemcpyAsync(dw, a2, bytes, cudaMemcpyDeviceToDevice, st));
+  }
+  return FLOW3D_OK;
+}
+
+}  // namespace f3d
+
+using namespace f3d;
+
+// ================================================================================================
+// solver object
+// ================================================================================================
+struct flow3d_solver {
+  size_t W = 0, H = 0, D = 0;
+  size_t ld = 0;        // full-resolution pitch
+  size_t vol = 0;       // floats per arena volume = ld*H*D
+  int device = 0;
+  float* arena = nullptr;
+  static constexpr int kVolumes = 19;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float last_ms[2] = {0.f, 0.f};
+  flow3d_level_callback cb = nullptr;
+  void* cb_user = nullptr;
+  float* buf(int i) const { return arena + (size_t)i * vol; }
+};
+
+// arena slots
+enum { B_F0 = 0, B_F1, B_F0L, B_F1L, B_FX, B_FY, B_FZ, B_FT, B_U, B_V, B_W, B_DU, B_DV, B_DW, B_TDU,
+       B_TDV, B_TDW, B_PHI, B_KSI };
+
+// The coarse-to-fine loop (optical_flow_e.cpp:179-473).  in0/in1: device frames with pitch in_ld.
+// On return u/v/w slots (tracked through the swaps) hold the full-resolution flow.
+static int run_pyramid(flow3d_solver* s, const float* in0, const float* in1, size_t in_ld,
+                       const flow3d_params* p, float** out_u, float** out_v, float** out_w,
+                       cudaStream_t st) {
+  const size_t full[3] = {s->W, s->H, s->D};
+  const Dims gfull = make_dims(full, s->ld);
+  float *F0 = s->buf(B_F0), *F1 = s->buf(B_F1), *f0l = s->buf(B_F0L), *f1l = s->buf(B_F1L);
+  float *fx = s->buf(B_FX), *fy = s->buf(B_FY), *fz = s->buf(B_FZ), *ft = s->buf(B_FT);
+  float *u = s->buf(B_U), *v = s->buf(B_V), *w = s->buf(B_W);
+  float *du = s->buf(B_DU), *dv = s->buf(B_DV), *dw = s->buf(B_DW);
+  float *tdu = s->buf(B_TDU), *tdv = s->buf(B_TDV), *tdw = s->buf(B_TDW);
+  float *phi = s->buf(B_PHI), *ksi = s->buf(B_KSI);
+
+  const size_t max_level = flow3d_max_warp_level(s->W, s->H, s->D, p->warp_scale_factor);
+  int level = (int)std::min(p->warp_levels_count, max_level) - 1;  // :180
+
+  // :213-257 pre-blur (or plain copy into the solver's own frames)
+  if (p->gaussian_sigma > 0.0) {
+    if (in_ld != s->ld) {  // bring to the solver pitch first
+      F3D_CUDA(cudaMemcpy2DAsync(f0l, s->ld * 4, in0, in_ld * 4, s->W * 4, s->H * s->D, cudaMemcpyDeviceToDevice, st));
+      F3D_CUDA(cudaMemcpy2DAsync(f1l, s->ld * 4, in1, in_ld * 4, s->W * 4, s->H * s->D, cudaMemcpyDeviceToDevice, st));
+      in0 = f0l;
+      in1 = f1l;
+    }
+    F3D_TRY(gauss_blur(in0, F0, tdu, gfull, p->gaussian_sigma, st));
+    F3D_TRY(gauss_blur(in1, F1, tdu, gfull, p->gaussian_sigma, st));
+  } else {
+    F3D_CUDA(cudaMemcpy2DAsync(F0, s->ld * 4, in0, in_ld * 4, s->W * 4, s->H * s->D, cudaMemcpyDeviceToDevice, st));
+    F3D_CUDA(cudaMemcpy2DAsync(F1, s->ld * 4, in1, in_ld * 4, s->W * 4, s->H * s->D, cudaMemcpyDeviceToDevice, st));
+  }
+
+  size_t prev[3] = {0, 0, 0};
+  size_t prev_ld = 0;
+  while (level >= 0) {  // :261
+    size_t cur[3];
+    float h[3];
+    flow3d_level_geometry(s->W, s->H, s->D, p->warp_scale_factor, level, cur, h);
+    const size_t ld = aligned_ld(cur[0]);
+    const Dims g = make_dims(cur, ld);
+    const size_t bytes = (size_t)g.ps * g.d * sizeof(float);
+
+    const float *pf0, *pf1;
+    if (level == 0) {  // :275-277
+      pf0 = F0;
+      pf1 = F1;
+    } else {  // :279-299, always from full resolution
+      F3D_TRY(resample(F0, full, s->ld, f0l, cur, ld, tdu, tdv, st));
+      F3D_TRY(resample(F1, full, s->ld, f1l, cur, ld, tdu, tdv, st));
+      pf0 = f0l;
+      pf1 = f1l;
+    }
+    if (prev[0] == 0) {  // :304-310
+      F3D_CUDA(cudaMemsetAsync(u, 0, bytes, st));
+      F3D_CUDA(cudaMemsetAsync(v, 0, bytes, st));
+      F3D_CUDA(cudaMemsetAsync(w, 0, bytes, st));
+    } else {  // :311-344 prolongation (values not rescaled)
+      F3D_TRY(resample(u, prev, prev_ld, du, cur, ld, tdu, tdv, st));
+      F3D_TRY(resample(v, prev, prev_ld, dv, cur, ld, tdu, tdv, st));
+      F3D_TRY(resample(w, prev, prev_ld, dw, cur, ld, tdu, tdv, st));
+      std::swap(u, du);
+      std::swap(v, dv);
+      std::swap(w, dw);
+    }
+    // :348-369 warp, fused with the derivative stencils the solver kernels would recompute
+    F3D_TRY(launch_warp_derivatives(pf0, pf1, u, v, w, g, h[0], h[1], h[2], fx, fy, fz, ft, st));
+    // :372-417
+    F3D_TRY(solve_level(fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, tdu, tdv, tdw, g, h,
+                        p->outer_iterations_count, p->inner_iterations_count, p->equation_alpha,
+                        p->equation_smoothness, p->equation_data, st));
+    // :420-438
+    F3D_TRY(launch_add3(u, v, w, du, dv, dw, g, st));
+    prev[0] = cur[0]; prev[1] = cur[1]; prev[2] = cur[2];
+    prev_ld = ld;
+    --level;
+    // :443-473 median of each component (through a temp, then swap)
+    {
+      size_t r = p->median_radius;
+      int rc = launch_median(u, tdu, g, (int)r, st);
+      if (rc == FLOW3D_OK) {
+        std::swap(u, tdu);
+        F3D_TRY(launch_median(v, tdu, g, (int)r, st));
+        std::swap(v, tdu);
+        F3D_TRY(launch_median(w, tdu, g, (int)r, st));
+        std::swap(w, tdu);
+      } else if (rc != FLOW3D_ERR_UNSUPPORTED) {
+        return rc;
+      } else {
+        return rc;  // unsupported radius: report instead of handing back an unfiltered/garbage flow
+      }
+    }
+    if (s->cb) {
+      F3D_CUDA(cudaStreamSynchronize(st));
+      s->cb(level + 1, cur, ld, u, v, w, s->cb_user);
+    }
+  }
+  *out_u = u;
+  *out_v = v;
+  *out_w = w;
+  return FLOW3D_OK;
+}
+
+static int check_params(const flow3d_params* p) {
+  if (!p) return FLOW3D_ERR_INVALID_ARG;
+  if (p->warp_levels_count == 0) return FLOW3D_ERR_INVALID_ARG;
+  if (!(p->warp_scale_factor > 0.f)) return FLOW3D_ERR_INVALID_ARG;
+  size_t r = p->median_radius;
+  if (r == 0) return FLOW3D_ERR_INVALID_ARG;
+  if (r != 1 && (r % 2 == 0)) r -= 1;
+  if (!(r == 1 || r == 3 || r == 5 || r == 7)) return FLOW3D_ERR_UNSUPPORTED;
+  if (p->gaussian_sigma > 0.f && (size_t)(3 * p->gaussian_sigma) > 32) return FLOW3D_ERR_UNSUPPORTED;
+  return FLOW3D_OK;
+}
+
+extern "C" {
+
+int flow3d_version(void) { return 100; }
+
+const char* flow3d_status_string(int status) {
+  switch (status) {
+    case FLOW3D_OK: return "ok";
+    case FLOW3D_ERR_INVALID_ARG: return "invalid argument";
+    case FLOW3D_ERR_UNSUPPORTED: return "unsupported parameter value";
+    case FLOW3D_ERR_CUDA: return "CUDA error";
+    case FLOW3D_ERR_NO_DEVICE: return "no CUDA device (there is no CPU fallback)";
+    case FLOW3D_ERR_OUT_OF_MEMORY: return "out of device memory";
+    case FLOW3D_ERR_NOT_INITIALIZED: return "solver not initialized";
+    default: return "unknown status";
+  }
+}
+
+const char* flow3d_last_cuda_error(void) { return g_last_error.c_str(); }
+
+int flow3d_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    note_cuda_error(e, "cudaGetDeviceCount");
+    cudaGetLastError();
+    return FLOW3D_ERR_NO_DEVICE;
+  }
+  return n;
+}
+
+void flow3d_default_params(flow3d_params* p) {  // src/main.cpp:77-85
+  if (!p) return;
+  p->warp_levels_count = 40;
+  p->warp_scale_factor = 0.95f;
+  p->outer_iterations_count = 40;
+  p->inner_iterations_count = 5;
+  p->equation_alpha = 7.5f;
+  p->equation_smoothness = 0.001f;
+  p->equation_data = 0.001f;
+  p->median_radius = 5;
+  p->gaussian_sigma = 2.0f;
+}
+
+uint64_t flow3d_launch_count(void) { return g_launches.load(); }
+void flow3d_reset_launch_count(void) { g_launches.store(0); }
+
+size_t flow3d_max_warp_level(size_t width, size_t height, size_t depth, float scale_factor) {
+  size_t r_width = 1, r_height = 1, r_depth = 1;
+  size_t level_counter = 1;
+  while (scale_factor < 1.f) {
+    const float scale = std::pow(scale_factor, static_cast<float>(level_counter));
+    r_width = static_cast<size_t>(std::ceil(width * scale));
+    r_height = static_cast<size_t>(std::ceil(height * scale));
+    r_depth = static_cast<size_t>(std::ceil(depth * scale));
+    if (r_width < 4 || r_height < 4 || r_depth < 4) break;
+    ++level_counter;
+  }
+  if (r_width == 1 || r_height == 1 || r_depth == 1) --level_counter;
+  return level_counter;
+}
+
+int flow3d_level_geometry(size_t width, size_t height, size_t depth, float scale_factor, int level,
+                          size_t dims[3], float h[3]) {
+  if (!dims || !h || level < 0) return FLOW3D_ERR_INVALID_ARG;
+  const float scale = std::pow(scale_factor, static_cast<float>(level));
+  dims[0] = static_cast<size_t>(std::ceil(width * scale));
+  dims[1] = static_cast<size_t>(std::ceil(height * scale));
+  dims[2] = static_cast<size_t>(std::ceil(depth * scale));
+  if (dims[0] == 0 || dims[1] == 0 || dims[2] == 0) return FLOW3D_ERR_INVALID_ARG;
+  h[0] = width / static_cast<float>(dims[0]);
+  h[1] = height / static_cast<float>(dims[1]);
+  h[2] = depth / static_cast<float>(dims[2]);
+  return FLOW3D_OK;
+}
+
+size_t flow3d_aligned_ld(size_t w) { return aligned_ld(w); }
+
+int flow3d_set_device(int device) {
+  F3D_CUDA(cudaSetDevice(device));
+  return FLOW3D_OK;
+}
+int flow3d_malloc(void** dev_ptr, size_t bytes) {
+  if (!dev_ptr) return FLOW3D_ERR_INVALID_ARG;
+  F3D_CUDA(cudaMalloc(dev_ptr, bytes));
+  return FLOW3D_OK;
+}
+int flow3d_free(void* dev_ptr) {
+  F3D_CUDA(cudaFree(dev_ptr));
+  return FLOW3D_OK;
+}
+int flow3d_memset(void* dev_ptr, int value, size_t bytes, void* stream) {
+  F3D_CUDA(cudaMemsetAsync(dev_ptr, value, bytes, S(stream)));
+  return FLOW3D_OK;
+}
+int flow3d_upload(const float* host, float* dev, const size_t dims[3], size_t ld, void* stream) {
+  if (!host) return FLOW3D_ERR_INVALID_ARG;
+  F3D_TRY(check_volume(dev, dims, ld));
+  F3D_CUDA(cudaMemcpy2DAsync(dev, ld * 4, host, dims[0] * 4, dims[0] * 4, dims[1] * dims[2],
+                             cudaMemcpyHostToDevice, S(stream)));
+  return FLOW3D_OK;
+}
+int flow3d_download(const float* dev, float* host, const size_t dims[3], size_t ld, void* stream) {
+  if (!host) return FLOW3D_ERR_INVALID_ARG;
+  F3D_TRY(check_volume(dev, dims, ld));
+  F3D_CUDA(cudaMemcpy2DAsync(host, dims[0] * 4, dev, ld * 4, dims[0] * 4, dims[1] * dims[2],
+                             cudaMemcpyDeviceToHost, S(stream)));
+  return FLOW3D_OK;
+}
+int flow3d_stream_synchronize(void* stream) {
+  F3D_CUDA(cudaStreamSynchronize(S(stream)));
+  return FLOW3D_OK;
+}
+
+// ---- stage wrappers ----------------------------------------------------------------------------
+int flow3d_gauss_blur(const float* in, float* out, float* tmp, const size_t dims[3], size_t ld,
+                      float sigma, void* stream) {
+  F3D_TRY(check_volume(in, dims, ld));
+  F3D_TRY(check_volume(out, dims, ld));
+  F3D_TRY(check_volume(tmp, dims, ld));
+  if (in == out || !(sigma > 0.f)) return FLOW3D_ERR_INVALID_ARG;
+  return gauss_blur(in, out, tmp, make_dims(dims, ld), sigma, S(stream));
+}
+
+int flow3d_resample(const float* in, const size_t in_dims[3], size_t in_ld, float* out,
+                    const size_t out_dims[3], size_t out_ld, float* tmp_a, float* tmp_b,
+                    void* stream) {
+  F3D_TRY(check_volume(in, in_dims, in_ld));
+  F3D_TRY(check_volume(out, out_dims, out_ld));
+  if (!tmp_a || !tmp_b || !aligned16(tmp_a) || !aligned16(tmp_b) || in == out) return FLOW3D_ERR_INVALID_ARG;
+  return resample(in, in_dims, in_ld, out, out_dims, out_ld, tmp_a, tmp_b, S(stream));
+}
+
+int flow3d_warp(const float* f0, const float* f1, const float* u, const float* v, const float* w,
+                const size_t dims[3], size_t ld, const float h[3], float* out, void* stream) {
+  const void* ps[] = {f0, f1, u, v, w, out};
+  for (const void* p : ps) F3D_TRY(check_volume(p, dims, ld));
+  if (!h || out == f1) return FLOW3D_ERR_INVALID_ARG;
+  return launch_warp(f0, f1, u, v, w, make_dims(dims, ld), h[0], h[1], h[2], out, S(stream));
+}
+
+int flow3d_derivatives(const float* f0, const float* f1w, const size_t dims[3], size_t ld,
+                       const float h[3], float* fx, float* fy, float* fz, float* ft, void* stream) {
+  const void* ps[] = {f0, f1w, fx, fy, fz, ft};
+  for (const void* p : ps) F3D_TRY(check_volume(p, dims, ld));
+  if (!h) return FLOW3D_ERR_INVALID_ARG;
+  return launch_derivatives(f0, f1w, make_dims(dims, ld), h[0], h[1], h[2], fx, fy, fz, ft, S(stream));
+}
+
+int flow3d_warp_derivatives(const float* f0, const float* f1, const float* u, const float* v,
+                            const float* w, const size_t dims[3], size_t ld, const float h[3],
+                            float* fx, float* fy, float* fz, float* ft, void* stream) {
+  const void* ps[] = {f0, f1, u, v, w, fx, fy, fz, ft};
+  for (const void* p : ps) F3D_TRY(check_volume(p, dims, ld));
+  if (!h) return FLOW3D_ERR_INVALID_ARG;
+  return launch_warp_derivatives(f0, f1, u, v, w, make_dims(dims, ld), h[0], h[1], h[2], fx, fy, fz, ft,
+                                 S(stream));
+}
+
+int flow3d_phi_ksi(const float* fx, const float* fy, const float* fz, const float* ft,
+                   const float* u, const float* v, const float* w, const float* du,
+                   const float* dv, const float* dw, const size_t dims[3], size_t ld,
+                   const float h[3], float eps_smooth, float eps_data, float* phi, float* ksi,
+                   void* stream) {
+  const void* ps[] = {fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi};
+  for (const void* p : ps) F3D_TRY(check_volume(p, dims, ld));
+  if (!h) return FLOW3D_ERR_INVALID_ARG;
+  return launch_phi_ksi(fx, fy, fz, ft, u, v, w, du, dv, dw, make_dims(dims, ld), h[0], h[1], h[2],
+                        eps_smooth, eps_data, phi, ksi, S(stream));
+}
+
+int flow3d_sweep(const float* fx, const float* fy, const float* fz, const float* ft,
+                 const float* u, const float* v, const float* w, const float* du, const float* dv,
+                 const float* dw, const float* phi, const float* ksi, const size_t dims[3],
+                 size_t ld, const float h[3], float alpha, float* du_out, float* dv_out,
+                 float* dw_out, void* stream) {
+  const void* ps[] = {fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, du_out, dv_out, dw_out};
+  for (const void* p : ps) F3D_TRY(check_volume(p, dims, ld));
+  if (!h || du_out == du || dv_out == dv || dw_out == dw) return FLOW3D_ERR_INVALID_ARG;
+  return launch_sweep(fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, make_dims(dims, ld), h[0], h[1],
+                      h[2], alpha, du_out, dv_out, dw_out, S(stream));
+}
+
+int flow3d_solve_level(const float* fx, const float* fy, const float* fz, const float* ft,
+                       const float* u, const float* v, const float* w, float* du, float* dv,
+                       float* dw, float* scratch, const size_t dims[3], size_t ld,
+                       const float h[3], size_t outer, size_t inner, float alpha, float eps_smooth,
+                       float eps_data, void* stream) {
+  const void* ps[] = {fx, fy, fz, ft, u, v, w, du, dv, dw, scratch};
+  for (const void* p : ps) F3D_TRY(check_volume(p, dims, ld));
+  if (!h) return FLOW3D_ERR_INVALID_ARG;
+  const Dims g = make_dims(dims, ld);
+  const size_t n = (size_t)g.ps * g.d;
+  return solve_level(fx, fy, fz, ft, u, v, w, du, dv, dw, scratch, scratch + n, scratch + 2 * n,
+                     scratch + 3 * n, scratch + 4 * n, g, h, outer, inner, alpha, eps_smooth, eps_data,
+                     S(stream));
+}
+
+int flow3d_add3(float* u, float* v, float* w, const float* du, const float* dv, const float* dw,
+                const size_t dims[3], size_t ld, void* stream) {
+  const void* ps[] = {u, v, w, du, dv, dw};
+  for (const void* p : ps) F3D_TRY(check_volume(p, dims, ld));
+  return launch_add3(u, v, w, du, dv, dw, make_dims(dims, ld), S(stream));
+}
+
+int flow3d_median(const float* in, float* out, const size_t dims[3], size_t ld, size_t radius,
+                  void* stream) {
+  F3D_TRY(check_volume(in, dims, ld));
+  F3D_TRY(check_volume(out, dims, ld));
+  if (in == out || radius == 0 || radius > 64) return FLOW3D_ERR_INVALID_ARG;
+  return launch_median(in, out, make_dims(dims, ld), (int)radius, S(stream));
+}
+
+// ---- solver ----------------------------------------------------------------------------------------
+size_t flow3d_solver_workspace_bytes(size_t width, size_t height, size_t depth) {
+  return aligned_ld(width) * height * depth * sizeof(float) * (size_t)flow3d_solver::kVolumes;
+}
+
+int flow3d_solver_create(size_t width, size_t height, size_t depth, int device, flow3d_solver** out) {
+  if (!out || width < 2 || height < 2 || depth < 2) return FLOW3D_ERR_INVALID_ARG;
+  if (width > (1u << 30) || height > (1u << 30) || depth > (1u << 30)) return FLOW3D_ERR_INVALID_ARG;
+  *out = nullptr;
+  int n = flow3d_device_count();
+  if (n <= 0) return FLOW3D_ERR_NO_DEVICE;
+  if (device < 0 || device >= n) return FLOW3D_ERR_INVALID_ARG;
+  F3D_CUDA(cudaSetDevice(device));
+  flow3d_solver* s = new flow3d_solver();
+  s->W = width; s->H = height; s->D = depth;
+  s->ld = aligned_ld(width);
+  s->vol = s->ld * height * depth;
+  s->device = device;
+  cudaError_t e = cudaMalloc(&s->arena, s->vol * sizeof(float) * (size_t)flow3d_solver::kVolumes);
+  if (e != cudaSuccess) {
+    note_cuda_error(e, "cudaMalloc(arena)");
+    cudaGetLastError();
+    delete s;
+    return FLOW3D_ERR_OUT_OF_MEMORY;
+  }
+  e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&s->ev[i]);
+  if (e != cudaSuccess) {
+    note_cuda_error(e, "stream/event create");
+    flow3d_solver_destroy(s);
+    return FLOW3D_ERR_CUDA;
+  }
+  *out = s;
+  return FLOW3D_OK;
+}
+
+int flow3d_solver_destroy(flow3d_solver* s) {
+  if (!s) return FLOW3D_OK;
+  cudaSetDevice(s->device);
+  for (int i = 0; i < 4; ++i)
+    if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  if (s->arena) cudaFree(s->arena);
+  delete s;
+  return FLOW3D_OK;
+}
+
+int flow3d_solver_set_level_callback(flow3d_solver* s, flow3d_level_callback cb, void* user) {
+  if (!s) return FLOW3D_ERR_NOT_INITIALIZED;
+  s->cb = cb;
+  s->cb_user = user;
+  return FLOW3D_OK;
+}
+
+int flow3d_solver_last_timing(const flow3d_solver* s, float ms[2]) {
+  if (!s) return FLOW3D_ERR_NOT_INITIALIZED;
+  if (!ms) return FLOW3D_ERR_INVALID_ARG;
+  ms[0] = s->last_ms[0];
+  ms[1] = s->last_ms[1];
+  return FLOW3D_OK;
+}
+
+int flow3d_solver_compute_device(flow3d_solver* s, const float* frame_0, const float* frame_1,
+                                 size_t ld, const flow3d_params* params, float* flow_u,
+                                 float* flow_v, float* flow_w, void* stream) {
+  if (!s) return FLOW3D_ERR_NOT_INITIALIZED;
+  F3D_TRY(check_params(params));
+  const size_t full[3] = {s->W, s->H, s->D};
+  const void* ps[] = {frame_0, frame_1, flow_u, flow_v, flow_w};
+  for (const void* p : ps) F3D_TRY(check_volume(p, full, ld));
+  F3D_CUDA(cudaSetDevice(s->device));
+  cudaStream_t st = S(stream);
+  F3D_CUDA(cudaEventRecord(s->ev[0], st));
+  float *u, *v, *w;
+  F3D_TRY(run_pyramid(s, frame_0, frame_1, ld, params, &u, &v, &w, st));
+  const size_t wb = s->W * 4, rows = s->H * s->D;
+  F3D_CUDA(cudaMemcpy2DAsync(flow_u, ld * 4, u, s->ld * 4, wb, rows, cudaMemcpyDeviceToDevice, st));
+  F3D_CUDA(cudaMemcpy2DAsync(flow_v, ld * 4, v, s->ld * 4, wb, rows, cudaMemcpyDeviceToDevice, st));
+  F3D_CUDA(cudaMemcpy2DAsync(flow_w, ld * 4, w, s->ld * 4, wb, rows, cudaMemcpyDeviceToDevice, st));
+  F3D_CUDA(cudaEventRecord(s->ev[1], st));
+  return FLOW3D_OK;
+}
+
+int flow3d_solver_compute_host(flow3d_solver* s, const float* frame_0, const float* frame_1,
+                               const flow3d_params* params, float* flow_u, float* flow_v,
+                               float* flow_w) {
+  if (!s) return FLOW3D_ERR_NOT_INITIALIZED;
+  if (!frame_0 || !frame_1 || !flow_u || !flow_v || !flow_w) return FLOW3D_ERR_INVALID_ARG;
+  F3D_TRY(check_params(params));
+  F3D_CUDA(cudaSetDevice(s->device));
+  cudaStream_t st = s->stream;
+  const size_t wb = s->W * 4, rows = s->H * s->D;
+  // same bracket as the reference's timer: H2D -> all levels -> D2H (optical_flow_e.cpp:169 -> :579)
+  F3D_CUDA(cudaEventRecord(s->ev[0], st));
+  float* in0 = s->buf(B_F0L);
+  float* in1 = s->buf(B_F1L);
+  F3D_CUDA(cudaMemcpy2DAsync(in0, s->ld * 4, frame_0, wb, wb, rows, cudaMemcpyHostToDevice, st));
+  F3D_CUDA(cudaMemcpy2DAsync(in1, s->ld * 4, frame_1, wb, wb, rows, cudaMemcpyHostToDevice, st));
+  F3D_CUDA(cudaEventRecord(s->ev[2], st));
+  float *u, *v, *w;
+  F3D_TRY(run_pyramid(s, in0, in1, s->ld, params, &u, &v, &w, st));
+  F3D_CUDA(cudaEventRecord(s->ev[3], st));
+  F3D_CUDA(cudaMemcpy2DAsync(flow_u, wb, u, s->ld * 4, wb, rows, cudaMemcpyDeviceToHost, st));
+  F3D_CUDA(cudaMemcpy2DAsync(flow_v, wb, v, s->ld * 4, wb, rows, cudaMemcpyDeviceToHost, st));
+  F3D_CUDA(cudaMemcpy2DAsync(flow_w, wb, w, s->ld * 4, wb, rows, cudaMemcpyDeviceToHost, st));
+  F3D_CUDA(cudaEventRecord(s->ev[1], st));
+  F3D_CUDA(cudaStreamSynchronize(st));
+  F3D_CUDA(cudaEventElapsedTime(&s->last_ms[0], s->ev[0], s->ev[1]));
+  F3D_CUDA(cudaEventElapsedTime(&s->last_ms[1], s->ev[2], s->ev[3]));
+  return FLOW3D_OK;
+}
+
+int flow3d_synth_pair(size_t width, size_t height, size_t depth, size_t z0, size_t nz, size_t ld,
+                      uint64_t seed, float* frame_0, float* frame_1, float* truth_u,
+                      float* truth_v, float* truth_w, void* stream) {
+  if (width == 0 || height == 0 || depth == 0 || ld < width) return FLOW3D_ERR_INVALID_ARG;
+  return launch_synth(width, height, depth, z0, nz, ld, seed, frame_0, frame_1, truth_u, truth_v,
+                      truth_w, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,203 @@
+/* flow3d_c.h -- C ABI of the B200-native dense 3D variational optical-flow solve.
+ *
+ * This is the drop-in boundary for the hot path of axruff/cuda-flow3d:
+ * plain pointers and sizes, no C++/torch types, every entry point returns an int status
+ * (0 = FLOW3D_OK, negative = error), never throws, never aborts.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference
+ * tree).  Stage functions work on DEVICE pointers; the solver object owns its device arena and
+ * offers a host-buffer call (the reference's OpticalFlowE::ComputeFlow contract) and a
+ * device-buffer call.
+ *
+ * Volume layout (all stage functions): x-fastest fp32, element (x,y,z) at  (z*h + y)*ld + x,
+ * `ld` = row pitch in floats, ld >= w, ld % 4 == 0, base pointer 16-byte aligned.  Columns
+ * [w, ld) are padding: never interpreted, may be overwritten.  The reference instead keeps every
+ * level in the top-left-front corner of a full-resolution pitched container
+ * (src/kernels/solve_3d.cu:26); that is a storage choice with identical results.
+ *
+ * `stream` arguments are cudaStream_t passed as void* (NULL = legacy default stream).
+ */
+#ifndef FLOW3D_C_H_
+#define FLOW3D_C_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLOW3D_OK 0
+#define FLOW3D_ERR_INVALID_ARG (-1)   /* null pointer, bad dims, misaligned ld/pointer */
+#define FLOW3D_ERR_UNSUPPORTED (-2)   /* e.g. median radius outside {1,3,5,7}, blur radius > 32 */
+#define FLOW3D_ERR_CUDA (-3)          /* a CUDA runtime call failed; see flow3d_last_cuda_error() */
+#define FLOW3D_ERR_NO_DEVICE (-4)     /* no CUDA device: there is NO CPU fallback */
+#define FLOW3D_ERR_OUT_OF_MEMORY (-5)
+#define FLOW3D_ERR_NOT_INITIALIZED (-6)
+
+/* The nine named solver parameters of the reference (src/main.cpp:77-85,157-165; read at
+ * src/optical_flow/optical_flow_e.cpp:150-158).  Same names, same types. */
+typedef struct flow3d_params {
+  size_t warp_levels_count;      /* default 40   */
+  float warp_scale_factor;       /* default 0.95 */
+  size_t outer_iterations_count; /* default 40   */
+  size_t inner_iterations_count; /* default 5    */
+  float equation_alpha;          /* default 7.5  */
+  float equation_smoothness;     /* default 0.001 */
+  float equation_data;           /* default 0.001 */
+  size_t median_radius;          /* default 5 (window edge length: 1 = off, 3, 5, 7) */
+  float gaussian_sigma;          /* default 2.0 (<= 0 = no pre-blur) */
+} flow3d_params;
+
+typedef struct flow3d_solver flow3d_solver; /* opaque */
+
+/* ---- misc ------------------------------------------------------------------------------- */
+int flow3d_version(void);
+const char* flow3d_status_string(int status);
+/* text of the last CUDA error seen by this thread's calls ("" if none) */
+const char* flow3d_last_cuda_error(void);
+/* number of visible CUDA devices, or a negative status */
+int flow3d_device_count(void);
+void flow3d_default_params(flow3d_params* p);
+/* kernels launched by this library since process start / last reset (bench.py's gpu_launches) */
+uint64_t flow3d_launch_count(void);
+void flow3d_reset_launch_count(void);
+
+/* ---- level schedule (host arithmetic only) ------------------------------------------------
+ * replaces OpticalFlowBase::GetMaxWarpLevel (src/optical_flow/optical_flow_base.cpp:31-56) */
+size_t flow3d_max_warp_level(size_t width, size_t height, size_t depth, float scale_factor);
+/* replaces the per-level size/spacing arithmetic of src/optical_flow/optical_flow_e.cpp:262-268;
+ * dims = {w,h,d} of `level`, h = {hx,hy,hz} */
+int flow3d_level_geometry(size_t width, size_t height, size_t depth, float scale_factor, int level,
+                          size_t dims[3], float h[3]);
+/* row pitch (floats) the solver uses for a level of width w */
+size_t flow3d_aligned_ld(size_t w);
+
+/* ---- device memory helpers (so callers need no CUDA headers) ------------------------------ */
+int flow3d_set_device(int device);
+int flow3d_malloc(void** dev_ptr, size_t bytes);
+int flow3d_free(void* dev_ptr);
+int flow3d_memset(void* dev_ptr, int value, size_t bytes, void* stream);
+/* copy a tight host volume (w*h*d floats) into a pitched device volume and back */
+int flow3d_upload(const float* host, float* dev, const size_t dims[3], size_t ld, void* stream);
+int flow3d_download(const float* dev, float* host, const size_t dims[3], size_t ld, void* stream);
+int flow3d_stream_synchronize(void* stream);
+
+/* ---- stage functions (device pointers) ----------------------------------------------------- */
+
+/* Separable Gaussian pre-blur, zero padding, taps from sigma exactly as the reference computes
+ * them.  Replaces CudaOperationConvolution3D::Execute
+ * (src/cuda_operations/entire_data/cuda_operation_convolution.cpp:134-184) and
+ * convolutionRows/Columns/SlicesKernel (src/kernels/convolution_3d.cu:75-372), with guarded
+ * edges (the reference kernels write out of bounds when a dimension is not a multiple of 4).
+ * in != out; tmp is a scratch volume of the same shape. */
+int flow3d_gauss_blur(const float* in, float* out, float* tmp, const size_t dims[3], size_t ld,
+                      float sigma, void* stream);
+
+/* Separable box (area-average) resample X -> Y -> Z, shrink or grow.  Replaces
+ * CudaOperationResample::Execute (.../cuda_operation_resample.cpp:72-106) and
+ * resample_{x,y,z}_3d (src/kernels/resample_3d.cu:28-161).
+ * tmp_a: >= flow3d_aligned_ld(out_w)*in_h*in_d floats, tmp_b: >= ld(out_w)*out_h*in_d floats. */
+int flow3d_resample(const float* in, const size_t in_dims[3], size_t in_ld, float* out,
+                    const size_t out_dims[3], size_t out_ld, float* tmp_a, float* tmp_b,
+                    void* stream);
+
+/* Backward trilinear warp of frame 1 by the flow; out-of-volume / NaN targets fall back to
+ * frame 0.  Replaces CudaOperationRegistration::Execute (.../cuda_operation_registration.cpp:
+ * 70-131) and registration_3d (src/kernels/registration_3d.cu:28-82).  out must not alias f1. */
+int flow3d_warp(const float* f0, const float* f1, const float* u, const float* v, const float* w,
+                const size_t dims[3], size_t ld, const float h[3], float* out, void* stream);
+
+/* Image derivatives of the (frame0, warped frame1) pair: fx, fy, fz (central differences of
+ * (f0+f1w)/(4h), mirror borders) and ft = f1w - f0.  These are the quantities the reference
+ * recomputes inside every launch (src/kernels/solve_3d.cu:220-233 and :425-438); computing them
+ * once per level gives bit-identical values. */
+int flow3d_derivatives(const float* f0, const float* f1w, const size_t dims[3], size_t ld,
+                       const float h[3], float* fx, float* fy, float* fz, float* ft, void* stream);
+
+/* Fused warp + derivatives: same results as flow3d_warp followed by flow3d_derivatives, without
+ * writing the warped volume. */
+int flow3d_warp_derivatives(const float* f0, const float* f1, const float* u, const float* v,
+                            const float* w, const size_t dims[3], size_t ld, const float h[3],
+                            float* fx, float* fy, float* fz, float* ft, void* stream);
+
+/* Robust weights phi (smoothness) and ksi (data).  Replaces compute_phi_ksi_3d
+ * (src/kernels/solve_3d.cu:33-262; launched at .../cuda_operation_solve.cpp:194-221). */
+int flow3d_phi_ksi(const float* fx, const float* fy, const float* fz, const float* ft,
+                   const float* u, const float* v, const float* w, const float* du,
+                   const float* dv, const float* dw, const size_t dims[3], size_t ld,
+                   const float h[3], float eps_smooth, float eps_data, float* phi, float* ksi,
+                   void* stream);
+
+/* One Jacobi sweep (du,dv,dw) -> (du_out,dv_out,dw_out).  Replaces solve_3d
+ * (src/kernels/solve_3d.cu:264-508; launched at .../cuda_operation_solve.cpp:223-257). */
+int flow3d_sweep(const float* fx, const float* fy, const float* fz, const float* ft,
+                 const float* u, const float* v, const float* w, const float* du, const float* dv,
+                 const float* dw, const float* phi, const float* ksi, const size_t dims[3],
+                 size_t ld, const float h[3], float alpha, float* du_out, float* dv_out,
+                 float* dw_out, void* stream);
+
+/* The whole inner solver of one level: du=dv=dw=0, then `outer` x (phi/ksi + `inner` sweeps).
+ * Replaces CudaOperationSolve::Execute (.../cuda_operation_solve.cpp:75-281).  On return
+ * du/dv/dw hold the final iterate.  scratch: 5 volumes of ld*h*d floats (phi, ksi, 3 ping-pong). */
+int flow3d_solve_level(const float* fx, const float* fy, const float* fz, const float* ft,
+                       const float* u, const float* v, const float* w, float* du, float* dv,
+                       float* dw, float* scratch, const size_t dims[3], size_t ld,
+                       const float h[3], size_t outer, size_t inner, float alpha, float eps_smooth,
+                       float eps_data, void* stream);
+
+/* u += du, v += dv, w += dw in one launch.  Replaces three add_3d launches
+ * (src/kernels/add_3d.cu:26-41; src/optical_flow/optical_flow_e.cpp:420-438). */
+int flow3d_add3(float* u, float* v, float* w, const float* du, const float* dv, const float* dw,
+                const size_t dims[3], size_t ld, void* stream);
+
+/* radius^3 median with mirror borders; radius = window edge length (1 = copy, even -> radius-1,
+ * supported 3/5/7).  Replaces CudaOperationMedian::Execute (.../cuda_operation_median.cpp:72-149)
+ * and median_3d (src/kernels/median_3d.cu:49-299).  in != out. */
+int flow3d_median(const float* in, float* out, const size_t dims[3], size_t ld, size_t radius,
+                  void* stream);
+
+/* ---- solver object -------------------------------------------------------------------------
+ * Replaces OpticalFlowE::{Initialize, ComputeFlow, Destroy}
+ * (src/optical_flow/optical_flow_e.cpp:42-49, 132-601, 603-622). */
+
+/* bytes of device memory a solver for a W x H x D volume allocates */
+size_t flow3d_solver_workspace_bytes(size_t width, size_t height, size_t depth);
+int flow3d_solver_create(size_t width, size_t height, size_t depth, int device,
+                         flow3d_solver** out);
+int flow3d_solver_destroy(flow3d_solver* s);
+
+/* Host-buffer solve = the reference's ComputeFlow contract: tight W*H*D fp32 host volumes in,
+ * three tight host volumes out; blocks until the results are in host memory. */
+int flow3d_solver_compute_host(flow3d_solver* s, const float* frame_0, const float* frame_1,
+                               const flow3d_params* params, float* flow_u, float* flow_v,
+                               float* flow_w);
+
+/* Device-buffer solve: inputs/outputs are device volumes with pitch `ld` (as laid out by
+ * flow3d_upload); asynchronous on `stream`. */
+int flow3d_solver_compute_device(flow3d_solver* s, const float* frame_0, const float* frame_1,
+                                 size_t ld, const flow3d_params* params, float* flow_u,
+                                 float* flow_v, float* flow_w, void* stream);
+
+/* milliseconds of the last compute call, measured with CUDA events: [0] whole call (host call:
+ * including H2D/D2H, the reference's own bracket optical_flow_e.cpp:169->579), [1] device-only */
+int flow3d_solver_last_timing(const flow3d_solver* s, float ms[2]);
+
+/* optional per-level observer for tests: called (after a stream sync) with the level's flow */
+typedef void (*flow3d_level_callback)(int level, const size_t dims[3], size_t ld,
+                                      const float* dev_u, const float* dev_v, const float* dev_w,
+                                      void* user);
+int flow3d_solver_set_level_callback(flow3d_solver* s, flow3d_level_callback cb, void* user);
+
+/* ---- synthetic test volumes ---------------------------------
+ * Analytic texture pair with a known rigid motion, generated on the device in double precision.
+ * z0/nz select a z-slab (for sharded generation); out_* may be NULL.  truth_* receive the
+ * ground-truth flow in the reference's convention (f1(x + flow) = f0(x)). */
+int flow3d_synth_pair(size_t width, size_t height, size_t depth, size_t z0, size_t nz, size_t ld,
+                      uint64_t seed, float* frame_0, float* frame_1, float* truth_u,
+                      float* truth_v, float* truth_w, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOW3D_C_H_ */

@@ -380,12 +380,17 @@ void o_sweep(const float* f0, const float* f1, const float* u, const float* v, c
         sumW = std::fmaf(azp, (wv[izp] + dw[izp]) - wc, sumW);
         sumW = std::fmaf(azm, (wv[izm] + dw[izm]) - wc, sumW);
 
-        // numerators: (-J14 - J12*dv) - J13*dw with rounded products, then fma(ksi, ., sum);
-        // denominators: fma(Jii, ksi, sumH); IEEE division.
+        // numerators: nvcc's PTX keeps J12*dv and J13*dw as separate mul.f32 + sub.f32, but those
+        // carry no .rn and ptxas (offline 12.9 and the driver JIT alike; checked in the SASS and
+        // against the reference kernels on a B200) contracts each pair:
+        //   n = fma(-J13, dw, fma(-J12, dv, -J14));   num = fma(ksi, n, sum);   den = fma(Jii, ksi, sumH)
         float k = ksi[c];
-        float r_du = std::fmaf(k, ((-J14) - J12 * dv[c]) - J13 * dw[c], sumU) / std::fmaf(J11, k, sumH);
-        float r_dv = std::fmaf(k, ((-J24) - J12 * r_du) - J23 * dw[c], sumV) / std::fmaf(J22, k, sumH);
-        float r_dw = std::fmaf(k, ((-J34) - J13 * r_du) - J23 * r_dv, sumW) / std::fmaf(J33, k, sumH);
+        float n_du = std::fmaf(-J13, dw[c], std::fmaf(-J12, dv[c], -J14));
+        float r_du = std::fmaf(k, n_du, sumU) / std::fmaf(J11, k, sumH);
+        float n_dv = std::fmaf(-J23, dw[c], std::fmaf(-J12, r_du, -J24));
+        float r_dv = std::fmaf(k, n_dv, sumV) / std::fmaf(J22, k, sumH);
+        float n_dw = std::fmaf(-J23, r_dv, std::fmaf(-J13, r_du, -J34));
+        float r_dw = std::fmaf(k, n_dw, sumW) / std::fmaf(J33, k, sumH);
 
         tdu[c] = r_du;
         tdv[c] = r_dv;
