@@ -1,0 +1,356 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the flow3d hot path on B200.
+
+Metric (BASELINE.json): Mvoxel/s per full pyramid flow solve = W*H*D / t_solve / 1e6, default
+parameters (src/main.cpp:77-85: 40 levels, scale 0.95, 40 outer x 5 inner sweeps, median 5, sigma 2).
+One "step" = one full coarse-to-fine solve of one synthetic volume pair.
+
+  python bench.py --gpus N --steps K --warmup W            our arm
+  python bench.py --impl reference --gpus N --steps K ...  the reference's own CUDA build (oracle/_ref)
+
+N=1 workload: configs[2], the synthetic 512^3 pair with known rigid motion (the largest single-GPU
+configuration of BASELINE.json).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SWEEP_BYTES = 52.0     # algorithmic bytes of one voxel-sweep: 10 reads + 3 writes, fp32
+PHIKSI_BYTES = 40.0    # one phi/ksi voxel update: 8 reads + 2 writes
+SEED = 20240521
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=0, help="cube edge (default 512)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1]))
+                    mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            os.remove(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """per-launch DRAM bytes of the sweep kernel from the committed ncu capture, if any"""
+    p = os.path.join(ROOT, "profiles", "sweep_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_baseline_sample(n, schedule_units, nthreads=None):
+    """Oracle (scalar C++ port, OpenMP) timed on a bounded sample: one outer iteration (phi/ksi + 5
+    sweeps) on an n^3 level, extrapolated to the whole default solve by voxel-passes."""
+    from oracle.oracle import Oracle
+    o = Oracle()
+    cores = o.num_threads() if nthreads is None else nthreads
+    o.set_num_threads(cores)
+    m = min(n, 256)  # bounded: 256^3 x 6 passes ~ 1e8 voxel-passes
+    rng = np.random.default_rng(0)
+    shape = (m, m, m)
+    f0 = (rng.random(shape, dtype=np.float32) * 255).astype(np.float32)
+    f1 = (rng.random(shape, dtype=np.float32) * 255).astype(np.float32)
+    z = [np.zeros(shape, np.float32) for _ in range(3)]
+    t = time.perf_counter()
+    o.solve_level(f0, f1, z[0], z[1], z[2], (1.0, 1.0, 1.0), 1, 5, 7.5, 0.001, 0.001)
+    dt = time.perf_counter() - t
+    passes_sample = 6.0 * m ** 3
+    rate = passes_sample / dt                      # voxel-passes / s
+    t_full = schedule_units / rate                 # seconds for the whole solve's solver passes
+    return {"value": (n ** 3) / t_full / 1e6, "unit": "Mvoxel/s", "cores": int(cores), "kind": "port",
+            "sample": "oracle solve_level: 1 outer iteration (phi/ksi + 5 sweeps) on %d^3 in %.2f s, "
+                      "extrapolated by voxel-passes (%.3g per full solve; solver = 98%% of the work)" %
+                      (m, dt, schedule_units)}
+
+
+def level_voxel_sum(pkg, W, H, D, P):
+    s = pkg.level_schedule(W, H, D, P["warp_scale_factor"], P["warp_levels_count"])
+    return float(sum(d[0] * d[1] * d[2] for _, d, _ in s)), len(s)
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """The reference's own CUDA build (the reference has no CPU path), one process on rank 0."""
+    if rank != 0:
+        return
+    from oracle import ref_runner
+    n = args.size or 512
+    base = {"impl": "reference", "metric": "Mvoxel/s per full pyramid flow solve", "unit": "Mvoxel/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+            "dtype": "f32", "data": "synthetic", "scaling": "weak", "vs_baseline": None,
+            "config": {"workload": "synthetic %d^3 pair, default parameters, reference CUDA build on ONE B200 "
+                                   "(it is single-GPU)" % n, "inputs_larger_than_l2": n >= 512}}
+    if not ref_runner.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}))
+        return
+    import cuda_flow3d_b200 as pkg
+    pkg.require_device()
+    f0, f1, _ = pkg.ops.synth_pair(n, n, n, SEED, truth=False)
+    warm = min(args.warmup, 1)  # module load/JIT is outside ComputeFlow; one warm solve is enough
+    sampler = ClockSampler(0)
+    sampler.start()
+    _, _, _, times, _ = ref_runner.run_reference(f0, f1, reps=warm + args.steps, want_output=False, timeout=6000)
+    clocks = sampler.stop()
+    t = times[warm:]
+    ms = 1000.0 * float(np.mean(t))
+    val = n ** 3 / (ms / 1000.0) / 1e6
+    base.update(value=val, ms_per_step=ms, clocks=clocks,
+                cpu_baseline={"value": val, "unit": "Mvoxel/s", "cores": 1, "kind": "reference",
+                              "sample": "unmodified reference sources (oracle/build_ref.sh), %d full solves of the "
+                                        "%d^3 pair on the B200, host-timed around ComputeFlow (H2D+levels+D2H); "
+                                        "the reference has no CPU implementation" % (len(t), n)},
+                e2e={"value": val, "unit": "Mvoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                gpu_launches=0, per_step_seconds=t)
+    print(json.dumps(base))
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import cuda_flow3d_b200 as pkg
+    L = pkg.load()
+    pkg.require_device()
+    torch.cuda.set_device(local_rank)
+    pkg._lib.check(L.flow3d_set_device(local_rank), "set_device")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n = args.size or 512
+    W = H = D = n
+    P = dict(pkg.DEFAULTS)
+    params = pkg.api.make_params(P)
+    ld = int(L.flow3d_aligned_ld(W))
+    vol = ld * H * D
+
+    # ---- resident inputs (generated on the device) and outputs --------------------------------------
+    dev = torch.device("cuda", local_rank)
+    f0 = torch.empty(vol, dtype=torch.float32, device=dev)
+    f1 = torch.empty(vol, dtype=torch.float32, device=dev)
+    outs = [torch.empty(vol, dtype=torch.float32, device=dev) for _ in range(3)]
+    st = torch.cuda.current_stream()
+    sp = C.c_void_p(st.cuda_stream)
+    pkg._lib.check(L.flow3d_synth_pair(W, H, D, 0, D, ld, SEED + rank, C.c_void_p(f0.data_ptr()),
+                                       C.c_void_p(f1.data_ptr()), None, None, None, sp), "synth")
+    solver = C.c_void_p()
+    pkg._lib.check(L.flow3d_solver_create(W, H, D, local_rank, C.byref(solver)), "solver_create")
+    pkg._lib.check(L.flow3d_solver_set_profiling(solver, 1), "profiling")
+
+    def step_device():
+        pkg._lib.check(L.flow3d_solver_compute_device(
+            solver, C.c_void_p(f0.data_ptr()), C.c_void_p(f1.data_ptr()), ld, C.byref(params),
+            C.c_void_p(outs[0].data_ptr()), C.c_void_p(outs[1].data_ptr()), C.c_void_p(outs[2].data_ptr()), sp),
+            "compute_device")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    L.flow3d_reset_launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_ms = np.zeros(8)
+    stage_units = np.zeros(8)
+    stage_launches = np.zeros(8)
+    e0.record(st)
+    for _ in range(args.steps):
+        step_device()
+        # per-stage event times of this step (queried after the step's last event completes)
+        ms = (C.c_float * 8)()
+        un = (C.c_double * 8)()
+        ln = (C.c_uint64 * 8)()
+        pkg._lib.check(L.flow3d_solver_stage_times(solver, ms, un, ln), "stage_times")
+        stage_ms += np.array(list(ms))
+        stage_units += np.array(list(un))
+        stage_launches += np.array(list(ln))
+    e1.record(st)
+    barrier()
+    clocks = sampler.stop()
+    launches = int(L.flow3d_launch_count())
+    t_ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([t_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_ms = float(t.item())
+    ms_per_step = t_ms / args.steps
+    value = world * (W * H * D) / (ms_per_step / 1000.0) / 1e6
+
+    # ---- e2e: the reference-shaped host call with pinned HOST buffers (H2D + D2H inside) ------------
+    e2e = None
+    if not args.no_e2e:
+        h0 = torch.empty((D, H, W), dtype=torch.float32, pin_memory=True)
+        h1 = torch.empty((D, H, W), dtype=torch.float32, pin_memory=True)
+        ho = [torch.empty((D, H, W), dtype=torch.float32, pin_memory=True) for _ in range(3)]
+        dims = pkg._lib.sz3((W, H, D))
+        pkg._lib.check(L.flow3d_download(C.c_void_p(f0.data_ptr()), C.c_void_p(h0.data_ptr()), dims, ld, sp), "dl")
+        pkg._lib.check(L.flow3d_download(C.c_void_p(f1.data_ptr()), C.c_void_p(h1.data_ptr()), dims, ld, sp), "dl")
+        torch.cuda.synchronize()
+
+        def step_host():
+            pkg._lib.check(L.flow3d_solver_compute_host(
+                solver, C.c_void_p(h0.data_ptr()), C.c_void_p(h1.data_ptr()), C.byref(params),
+                C.c_void_p(ho[0].data_ptr()), C.c_void_p(ho[1].data_ptr()), C.c_void_p(ho[2].data_ptr())),
+                "compute_host")
+
+        step_host()  # warm
+        barrier()
+        tot = 0.0
+        ne = max(1, min(args.steps, 2))
+        for _ in range(ne):
+            step_host()
+            ms2 = (C.c_float * 2)()
+            L.flow3d_solver_last_timing(solver, ms2)
+            tot += float(ms2[0])  # CUDA events: before H2D -> after D2H (the reference's own bracket)
+        e_ms = tot / ne
+        if dist is not None:
+            t = torch.tensor([e_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_ms = float(t.item())
+        e2e = {"value": world * (W * H * D) / (e_ms / 1000.0) / 1e6, "unit": "Mvoxel/s",
+               "h2d_bytes_per_step": 2 * W * H * D * 4, "d2h_bytes_per_step": 3 * W * H * D * 4,
+               "ms_per_step": e_ms, "steps": ne, "host_memory": "pinned"}
+        # sanity: the device-resident and host paths must agree bit for bit
+        chk = torch.empty((D, H, W), dtype=torch.float32)
+        pkg._lib.check(L.flow3d_download(C.c_void_p(outs[0].data_ptr()), C.c_void_p(chk.data_ptr()), dims, ld, sp), "dl")
+        torch.cuda.synchronize()
+        e2e["host_equals_device_result"] = bool(torch.equal(chk, ho[0]))
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        sweep_s = stage_ms[4] / 1000.0
+        achieved = SWEEP_BYTES * stage_units[4] / sweep_s / 1e9 if sweep_s > 0 else 0.0
+        traffic = ncu_traffic()
+        nsum, nlev = level_voxel_sum(pkg, W, H, D, P)
+        names = ["blur", "resample", "warp_derivs", "phi_ksi", "sweep", "update", "median", "copy"]
+        line = {
+            "metric": "Mvoxel/s per full pyramid flow solve", "value": value, "unit": "Mvoxel/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "synthetic %d^3 pair with known rigid motion (BASELINE configs[2]), default "
+                                   "parameters: %d levels x 40 outer x 5 inner sweeps, median 5, sigma 2" % (n, nlev),
+                       "parallelism": "1 GPU" if world == 1 else "%d independent replicas (one volume pair per GPU)" % world,
+                       "inputs_larger_than_l2": bool(vol * 4 > 126e6), "level_voxels": nsum,
+                       "parity": "bit-identical to the reference CUDA build (tests/)"},
+            "clocks": clocks, "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "sweep_kernel (one Jacobi sweep)", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                         "peak_source": peak_src,
+                         "algorithmic_bytes_per_voxel_sweep": SWEEP_BYTES,
+                         "voxel_sweeps": stage_units[4], "launches": stage_launches[4],
+                         "avg_launch_ms": stage_ms[4] / max(1.0, stage_launches[4]),
+                         "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                         "traffic_note": traffic.get("note") if traffic else "no ncu capture yet"},
+            "stage_ms_per_step": {k: float(v) / args.steps for k, v in zip(names, stage_ms)},
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            solver_passes = nsum * (P["outer_iterations_count"] * (1 + P["inner_iterations_count"]))
+            try:
+                line["cpu_baseline"] = cpu_baseline_sample(n, solver_passes)
+            except Exception as ex:  # the bench line must still print
+                line["cpu_baseline"] = {"error": repr(ex)}
+        print(json.dumps(line))
+    L.flow3d_solver_destroy(solver)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -86,6 +86,8 @@ SIGNATURES = {
     "flow3d_solver_compute_device": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.POINTER(Params), _vp, _vp,
                                                _vp, _vp]),
     "flow3d_solver_last_timing": (C.c_int, [_vp, C.c_float * 2]),
+    "flow3d_solver_set_profiling": (C.c_int, [_vp, C.c_int]),
+    "flow3d_solver_stage_times": (C.c_int, [_vp, C.c_float * 8, C.c_double * 8, C.c_uint64 * 8]),
     "flow3d_solver_set_level_callback": (C.c_int, [_vp, LEVEL_CALLBACK, _vp]),
     "flow3d_synth_pair": (C.c_int, [C.c_size_t] * 6 + [C.c_uint64] + [_vp] * 6),
 }

@@ -43,6 +43,53 @@ int sm_count() {
   return cached;
 }
 
+// Stage timer: mark(tag) records an event; the time until the next mark belongs to `tag`.
+struct StageTimer {
+  bool enabled = false;
+  std::vector<cudaEvent_t> pool;
+  std::vector<int> tags;
+  size_t used = 0;
+  float ms[FLOW3D_STAGE_COUNT] = {0};
+  double units[FLOW3D_STAGE_COUNT] = {0};
+  uint64_t launches[FLOW3D_STAGE_COUNT] = {0};
+  uint64_t launch_mark = 0;
+  int cur_tag = -1;
+  void reset() {
+    used = 0;
+    tags.clear();
+    cur_tag = -1;
+    for (int i = 0; i < FLOW3D_STAGE_COUNT; ++i) { ms[i] = 0; units[i] = 0; launches[i] = 0; }
+  }
+  void mark(int tag, cudaStream_t st, double work = 0.0) {
+    if (!enabled) return;
+    const uint64_t now = g_launches.load(std::memory_order_relaxed);
+    if (cur_tag >= 0) launches[cur_tag] += now - launch_mark;
+    launch_mark = now;
+    cur_tag = tag;
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) { enabled = false; return; }
+      pool.push_back(e);
+    }
+    cudaEventRecord(pool[used++], st);
+    tags.push_back(tag);
+    if (tag >= 0) units[tag] += work;
+  }
+  // call after the stream has been synchronized; the last mark must be an end marker (tag -1)
+  void finish() {
+    if (!enabled) return;
+    for (size_t i = 0; i + 1 < used; ++i) {
+      if (tags[i] < 0) continue;
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, pool[i], pool[i + 1]) == cudaSuccess) ms[tags[i]] += t;
+    }
+  }
+  void destroy() {
+    for (cudaEvent_t e : pool) cudaEventDestroy(e);
+    pool.clear();
+  }
+};
+
 #define F3D_CUDA(call)                                   \
   do {                                                   \
     cudaError_t e_ = (call);                             \
@@ -108,16 +155,20 @@ static int solve_level(const float* fx, const float* fy, const float* fz, const 
                        const float* u, const float* v, const float* w, float* du, float* dv,
                        float* dw, float* phi, float* ksi, float* tdu, float* tdv, float* tdw, Dims g,
                        const float h[3], size_t outer, size_t inner, float alpha, float eps_s,
-                       float eps_d, cudaStream_t st) {
+                       float eps_d, cudaStream_t st, StageTimer* tm = nullptr) {
   const size_t bytes = (size_t)g.ps * g.d * sizeof(float);
+  const double nvox = (double)g.w * g.h * g.d;
+  if (tm) tm->mark(FLOW3D_STAGE_UPDATE, st);
   // cuda_operation_solve.cpp:183-188
   F3D_CUDA(cudaMemsetAsync(du, 0, bytes, st));
   F3D_CUDA(cudaMemsetAsync(dv, 0, bytes, st));
   F3D_CUDA(cudaMemsetAsync(dw, 0, bytes, st));
   float *a0 = du, *a1 = dv, *a2 = dw, *b0 = tdu, *b1 = tdv, *b2 = tdw;
   for (size_t i = 0; i < outer; ++i) {  // :194-257
+    if (tm) tm->mark(FLOW3D_STAGE_PHI_KSI, st, nvox);
     F3D_TRY(launch_phi_ksi(fx, fy, fz, ft, u, v, w, a0, a1, a2, g, h[0], h[1], h[2], eps_s, eps_d, phi,
                            ksi, st));
+    if (tm) tm->mark(FLOW3D_STAGE_SWEEP, st, nvox * (double)inner);
     for (size_t j = 0; j < inner; ++j) {
       F3D_TRY(launch_sweep(fx, fy, fz, ft, u, v, w, a0, a1, a2, phi, ksi, g, h[0], h[1], h[2], alpha,
                            b0, b1, b2, st));
@@ -126,6 +177,7 @@ static int solve_level(const float* fx, const float* fy, const float* fz, const 
       std::swap(a2, b2);
     }
   }
+  if (tm) tm->mark(FLOW3D_STAGE_UPDATE, st);
   if (a0 != du) {  // odd number of sweeps: bring the iterate home
     F3D_CUDA(cudaMemcpyAsync(du, a0, bytes, cudaMemcpyDeviceToDevice, st));
     F3D_CUDA(cudaMemcpyAsync(dv, a1, bytes, cudaMemcpyDeviceToDevice, st));
@@ -153,6 +205,7 @@ struct flow3d_solver {
   float last_ms[2] = {0.f, 0.f};
   flow3d_level_callback cb = nullptr;
   void* cb_user = nullptr;
+  StageTimer timer;
   float* buf(int i) const { return arena + (size_t)i * vol; }
 };
 
@@ -177,7 +230,10 @@ static int run_pyramid(flow3d_solver* s, const float* in0, const float* in1, siz
   const size_t max_level = flow3d_max_warp_level(s->W, s->H, s->D, p->warp_scale_factor);
   int level = (int)std::min(p->warp_levels_count, max_level) - 1;  // :180
 
+  StageTimer* tm = &s->timer;
+  const double nfull = (double)s->W * s->H * s->D;
   // :213-257 pre-blur (or plain copy into the solver's own frames)
+  tm->mark(FLOW3D_STAGE_BLUR, st, 2.0 * nfull);
   if (p->gaussian_sigma > 0.0) {
     if (in_ld != s->ld) {  // bring to the solver pitch first
       F3D_CUDA(cudaMemcpy2DAsync(f0l, s->ld * 4, in0, in_ld * 4, s->W * 4, s->H * s->D, cudaMemcpyDeviceToDevice, st));
@@ -202,6 +258,8 @@ static int run_pyramid(flow3d_solver* s, const float* in0, const float* in1, siz
     const Dims g = make_dims(cur, ld);
     const size_t bytes = (size_t)g.ps * g.d * sizeof(float);
 
+    const double nvox = (double)cur[0] * cur[1] * cur[2];
+    tm->mark(FLOW3D_STAGE_RESAMPLE, st, 5.0 * nvox);
     const float *pf0, *pf1;
     if (level == 0) {  // :275-277
       pf0 = F0;
@@ -225,17 +283,20 @@ static int run_pyramid(flow3d_solver* s, const float* in0, const float* in1, siz
       std::swap(w, dw);
     }
     // :348-369 warp, fused with the derivative stencils the solver kernels would recompute
+    tm->mark(FLOW3D_STAGE_WARP, st, nvox);
     F3D_TRY(launch_warp_derivatives(pf0, pf1, u, v, w, g, h[0], h[1], h[2], fx, fy, fz, ft, st));
     // :372-417
     F3D_TRY(solve_level(fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, tdu, tdv, tdw, g, h,
                         p->outer_iterations_count, p->inner_iterations_count, p->equation_alpha,
-                        p->equation_smoothness, p->equation_data, st));
+                        p->equation_smoothness, p->equation_data, st, tm));
     // :420-438
+    tm->mark(FLOW3D_STAGE_UPDATE, st, nvox);
     F3D_TRY(launch_add3(u, v, w, du, dv, dw, g, st));
     prev[0] = cur[0]; prev[1] = cur[1]; prev[2] = cur[2];
     prev_ld = ld;
     --level;
     // :443-473 median of each component (through a temp, then swap)
+    tm->mark(FLOW3D_STAGE_MEDIAN, st, 3.0 * nvox);
     {
       size_t r = p->median_radius;
       int rc = launch_median(u, tdu, g, (int)r, st);
@@ -251,6 +312,7 @@ static int run_pyramid(flow3d_solver* s, const float* in0, const float* in1, siz
         return rc;  // unsupported radius: report instead of handing back an unfiltered/garbage flow
       }
     }
+    tm->mark(-1, st);
     if (s->cb) {
       F3D_CUDA(cudaStreamSynchronize(st));
       s->cb(level + 1, cur, ld, u, v, w, s->cb_user);
@@ -528,6 +590,7 @@ int flow3d_solver_destroy(flow3d_solver* s) {
   for (int i = 0; i < 4; ++i)
     if (s->ev[i]) cudaEventDestroy(s->ev[i]);
   if (s->stream) cudaStreamDestroy(s->stream);
+  s->timer.destroy();
   if (s->arena) cudaFree(s->arena);
   delete s;
   return FLOW3D_OK;
@@ -558,13 +621,16 @@ int flow3d_solver_compute_device(flow3d_solver* s, const float* frame_0, const f
   for (const void* p : ps) F3D_TRY(check_volume(p, full, ld));
   F3D_CUDA(cudaSetDevice(s->device));
   cudaStream_t st = S(stream);
+  s->timer.reset();
   F3D_CUDA(cudaEventRecord(s->ev[0], st));
   float *u, *v, *w;
   F3D_TRY(run_pyramid(s, frame_0, frame_1, ld, params, &u, &v, &w, st));
   const size_t wb = s->W * 4, rows = s->H * s->D;
+  s->timer.mark(FLOW3D_STAGE_COPY, st);
   F3D_CUDA(cudaMemcpy2DAsync(flow_u, ld * 4, u, s->ld * 4, wb, rows, cudaMemcpyDeviceToDevice, st));
   F3D_CUDA(cudaMemcpy2DAsync(flow_v, ld * 4, v, s->ld * 4, wb, rows, cudaMemcpyDeviceToDevice, st));
   F3D_CUDA(cudaMemcpy2DAsync(flow_w, ld * 4, w, s->ld * 4, wb, rows, cudaMemcpyDeviceToDevice, st));
+  s->timer.mark(-1, st);
   F3D_CUDA(cudaEventRecord(s->ev[1], st));
   return FLOW3D_OK;
 }
@@ -579,7 +645,9 @@ int flow3d_solver_compute_host(flow3d_solver* s, const float* frame_0, const flo
   cudaStream_t st = s->stream;
   const size_t wb = s->W * 4, rows = s->H * s->D;
   // same bracket as the reference's timer: H2D -> all levels -> D2H (optical_flow_e.cpp:169 -> :579)
+  s->timer.reset();
   F3D_CUDA(cudaEventRecord(s->ev[0], st));
+  s->timer.mark(FLOW3D_STAGE_COPY, st);
   float* in0 = s->buf(B_F0L);
   float* in1 = s->buf(B_F1L);
   F3D_CUDA(cudaMemcpy2DAsync(in0, s->ld * 4, frame_0, wb, wb, rows, cudaMemcpyHostToDevice, st));
@@ -588,13 +656,39 @@ int flow3d_solver_compute_host(flow3d_solver* s, const float* frame_0, const flo
   float *u, *v, *w;
   F3D_TRY(run_pyramid(s, in0, in1, s->ld, params, &u, &v, &w, st));
   F3D_CUDA(cudaEventRecord(s->ev[3], st));
+  s->timer.mark(FLOW3D_STAGE_COPY, st);
   F3D_CUDA(cudaMemcpy2DAsync(flow_u, wb, u, s->ld * 4, wb, rows, cudaMemcpyDeviceToHost, st));
   F3D_CUDA(cudaMemcpy2DAsync(flow_v, wb, v, s->ld * 4, wb, rows, cudaMemcpyDeviceToHost, st));
   F3D_CUDA(cudaMemcpy2DAsync(flow_w, wb, w, s->ld * 4, wb, rows, cudaMemcpyDeviceToHost, st));
+  s->timer.mark(-1, st);
   F3D_CUDA(cudaEventRecord(s->ev[1], st));
   F3D_CUDA(cudaStreamSynchronize(st));
+  s->timer.finish();
   F3D_CUDA(cudaEventElapsedTime(&s->last_ms[0], s->ev[0], s->ev[1]));
   F3D_CUDA(cudaEventElapsedTime(&s->last_ms[1], s->ev[2], s->ev[3]));
+  return FLOW3D_OK;
+}
+
+int flow3d_solver_set_profiling(flow3d_solver* s, int enable) {
+  if (!s) return FLOW3D_ERR_NOT_INITIALIZED;
+  s->timer.enabled = enable != 0;
+  s->timer.reset();
+  return FLOW3D_OK;
+}
+
+int flow3d_solver_stage_times(flow3d_solver* s, float ms[FLOW3D_STAGE_COUNT],
+                              double units[FLOW3D_STAGE_COUNT], uint64_t launches[FLOW3D_STAGE_COUNT]) {
+  if (!s) return FLOW3D_ERR_NOT_INITIALIZED;
+  if (!ms || !units || !launches) return FLOW3D_ERR_INVALID_ARG;
+  if (s->timer.used && s->timer.ms[FLOW3D_STAGE_SWEEP] == 0.f) {  // device-buffer call: not finished yet
+    F3D_CUDA(cudaEventSynchronize(s->timer.pool[s->timer.used - 1]));
+    s->timer.finish();
+  }
+  for (int i = 0; i < FLOW3D_STAGE_COUNT; ++i) {
+    ms[i] = s->timer.ms[i];
+    units[i] = s->timer.units[i];
+    launches[i] = s->timer.launches[i];
+  }
   return FLOW3D_OK;
 }
 

@@ -183,6 +183,23 @@ int flow3d_solver_compute_device(flow3d_solver* s, const float* frame_0, const f
  * including H2D/D2H, the reference's own bracket optical_flow_e.cpp:169->579), [1] device-only */
 int flow3d_solver_last_timing(const flow3d_solver* s, float ms[2]);
 
+/* Per-stage device timing (CUDA events on the solve's stream), off by default.  When enabled, each
+ * compute call accumulates, per stage, the elapsed milliseconds and the units of work processed:
+ * voxels for every stage (FLOW3D_STAGE_SWEEP counts voxel-sweeps = voxels x sweeps, the unit of
+ * SURVEY.md 8d; FLOW3D_STAGE_PHI_KSI counts voxel-updates).  Query after the call has finished. */
+#define FLOW3D_STAGE_BLUR 0
+#define FLOW3D_STAGE_RESAMPLE 1
+#define FLOW3D_STAGE_WARP 2
+#define FLOW3D_STAGE_PHI_KSI 3
+#define FLOW3D_STAGE_SWEEP 4
+#define FLOW3D_STAGE_UPDATE 5   /* memset of du + flow update */
+#define FLOW3D_STAGE_MEDIAN 6
+#define FLOW3D_STAGE_COPY 7     /* H2D/D2H or D2D staging copies */
+#define FLOW3D_STAGE_COUNT 8
+int flow3d_solver_set_profiling(flow3d_solver* s, int enable);
+int flow3d_solver_stage_times(flow3d_solver* s, float ms[FLOW3D_STAGE_COUNT],
+                              double units[FLOW3D_STAGE_COUNT], uint64_t launches[FLOW3D_STAGE_COUNT]);
+
 /* optional per-level observer for tests: called (after a stream sync) with the level's flow */
 typedef void (*flow3d_level_callback)(int level, const size_t dims[3], size_t ld,
                                       const float* dev_u, const float* dev_v, const float* dev_w,

@@ -6,9 +6,9 @@
 # <exe dir>/kernels/.  Excluded (do not build with CUDA 12.9 / off the hot path): partial_data/*,
 # optical_flow_p.*, solve_p_3d.cu, registration_p_3d.cu, utils/gl/*, visualization.*, main.cpp.
 #
-# Also emits kernels_guarded/: identical PTX except that convolution_3d.cu is compiled from a
-# temporary copy with y/z(x) bounds guards added to the three blur kernels (the
-# shipped kernels write out of bounds when a dimension is not a multiple of 4).
+# Also emits kernels_guarded/: the same kernels compiled from temporary copies with bounds guards
+# (the shipped blur kernels write out of bounds when a dimension is not a multiple of 4,
+# and the shipped median reads a wild address on thin volumes; details below).
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 REF="${REFERENCE_ROOT:-/root/reference}"
@@ -48,32 +48,49 @@ for k in add_3d median_3d convolution_3d registration_3d resample_3d solve_3d; d
   cp "$OUT/kernels/$k.ptx" "$OUT/kernels_guarded/$k.ptx"
 done
 
-# guarded blur variant (temporary patched copy, never committed)
+# guarded variants (temporary patched copies, never committed):
+#  * convolution_3d.cu: the three blur kernels get bounds guards on the two non-convolved axes;
+#  * median_3d.cu, solve_3d.cu: the IND() macro clamps its coordinates to the level extent.  The
+#    shipped kernels mirror halo cells as `2*dim - i - 2`, which goes negative (-> a wild size_t
+#    index) for cells beyond 2*dim-2; those cells are never used by an in-range voxel, but the LOAD
+#    faults on a B200 (depth 5, blockDim.z 4 => illegal address in median_3d on the 584x388x5 pair).
+#    Clamping changes no value that any output depends on.
 TMP="$(mktemp -d)"
-python3 - "$REF/src/kernels/convolution_3d.cu" "$TMP/convolution_3d.cu" <<'PY'
-import re, sys
-src = open(sys.argv[1]).read()
+python3 - "$REF/src/kernels" "$TMP" <<'PY'
+import sys
+src_dir, tmp = sys.argv[1], sys.argv[2]
+src = open(src_dir + "/convolution_3d.cu").read()
 guards = {
     "convolutionRowsKernel": "    if (baseY >= imageH || baseZ >= imageD) return;\n",
     "convolutionColumnsKernel": "    if (baseX >= imageW || baseZ >= imageD) return;\n",
     "convolutionSlicesKernel": "    if (baseX >= imageW || baseY >= imageH) return;\n",
 }
-# insert each guard right after the declaration of baseZ inside the named kernel.  The guard sits
-# before __syncthreads(); whole (y,z) [or (x,z)/(x,y)] thread groups that leave never shared data
-# with in-range threads along the convolved axis, but they do share the barrier -- so instead of
-# returning we predicate the global loads/stores: rewrite to a flag.
-out = []
-pos = 0
+# whole thread groups that leave share no shared-memory cell with in-range threads (s_Data is
+# indexed by the two guarded thread coordinates) and exited threads do not block the barrier.
+ins = []
 for name, guard in guards.items():
     k = src.index("void " + name)
-    b = src.index("const int baseZ", k)
-    e = src.index("\n", b) + 1
-    out.append((e, guard))
-res = src
-for e, guard in sorted(out, reverse=True):
-    res = res[:e] + guard + res[e:]
-open(sys.argv[2], "w").write(res)
+    last = max(src.index("const int base" + ax, k) for ax in "XYZ")
+    ins.append((src.index("\n", last) + 1, guard))
+for e, guard in sorted(ins, reverse=True):
+    src = src[:e] + guard + src[e:]
+open(tmp + "/convolution_3d.cu", "w").write(src)
+
+helper = """
+__device__ __forceinline__ size_t f3d_clamp(long long v, size_t n) {
+  return v < 0 ? 0 : (v >= (long long)n ? n - 1 : (size_t)v);
+}
+#undef IND
+#define IND(X, Y, Z) ((f3d_clamp((long long)(Z), depth) * container_size.height + f3d_clamp((long long)(Y), height)) * (container_size.pitch / sizeof(float)) + f3d_clamp((long long)(X), width))
+"""
+for name in ("median_3d.cu", "solve_3d.cu"):
+    s = open(src_dir + "/" + name).read()
+    k = s.index("__constant__ DataSize4 container_size;")
+    e = s.index("\n", k) + 1
+    open(tmp + "/" + name, "w").write(s[:e] + helper + s[e:])
 PY
-"$CUDA/bin/nvcc" -ptx -std=c++11 -w -I"$REF" -I"$CUDA/include" "$TMP/convolution_3d.cu" -o "$OUT/kernels_guarded/convolution_3d.ptx"
+for k in convolution_3d median_3d solve_3d; do
+  "$CUDA/bin/nvcc" -ptx -std=c++11 -w -I"$REF" -I"$CUDA/include" "$TMP/$k.cu" -o "$OUT/kernels_guarded/$k.ptx"
+done
 rm -rf "$TMP" "$OUT/obj"
 echo "reference built into $OUT"
