@@ -8,6 +8,8 @@
 // (z-marching warps, vector loads, register-rotated z neighbours, shuffle x neighbours, per-level
 // precomputed image derivatives) is new.  A sensitivity study shows that merely changing
 // FMA contraction moves the final 128^3 flow by up to 9e-3 voxel, so this is what the 1e-3 gate needs.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace f3d {
@@ -56,6 +58,12 @@ __device__ __forceinline__ void stv(float* p, const Vec<VEC>& r) {
   }
 }
 
+// L2 prefetch of the cache line(s) this thread will load `pf` planes ahead: converts the DRAM
+// latency of the z-march into an L2 hit without holding registers for data in flight.
+__device__ __forceinline__ void prefetch_l2(const float* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 template <int VEC>
 __device__ __forceinline__ Vec<VEC> addv(const Vec<VEC>& a, const Vec<VEC>& b) {
   Vec<VEC> r;
@@ -76,6 +84,7 @@ struct SweepArgs {
   Dims g;
   float hx, hy, hz, alpha;
   int zchunk;
+  int pf;  // prefetch distance in planes (0 = off)
 };
 
 // x-neighbour values of a VEC-wide register group: left[i] / right[i] are the values at x-1 / x+1
@@ -104,7 +113,7 @@ __device__ __forceinline__ void x_neighbours(const Vec<VEC>& c, float halo, int 
 // S = u + du (one rounded add per voxel, shared by all six consumers of that voxel) and phi are
 // register-rotated along z; y neighbours are read straight from global memory (L1-resident: they
 // are the centre rows of the adjacent warps of the same CTA).
-template <int VEC>
+template <int VEC, int UNROLL>
 __global__ void __launch_bounds__(128) sweep_kernel(const SweepArgs a) {
   const Dims g = a.g;
   const int lane = threadIdx.x;
@@ -119,13 +128,17 @@ __global__ void __launch_bounds__(128) sweep_kernel(const SweepArgs a) {
 
   const int ym = mirror_idx(y - 1, g.h);
   const int yp = mirror_idx(y + 1, g.h);
-  // halo column of this lane (only lanes 0 and 31 use it)
-  const int xh = (lane == 0) ? mirror_idx(x0 - 1, g.w) : mirror_idx(x0 + VEC, g.w);
-  const bool halo_lane = (lane == 0) || (lane == 31);
+  // halo column of this lane: lane 0 -> x0-1, lane 31 -> x0+VEC (mirrored at the faces); the other
+  // lanes re-read their own first element (an L1 hit) so that the load needs no branch
+  const int xh = (lane == 0) ? mirror_idx(x0 - 1, g.w) : ((lane == 31) ? mirror_idx(x0 + VEC, g.w) : x0);
 
-  const long long row_c = (long long)y * g.ld;
-  const long long row_m = (long long)ym * g.ld;
-  const long long row_p = (long long)yp * g.ld;
+  // 32-bit element offsets (volumes hold < 2^32 elements; checked by the launcher): one
+  // IMAD.WIDE per load instead of a 64-bit add pair
+  const unsigned ps = (unsigned)g.ps;
+  const unsigned row_c = (unsigned)y * g.ld + x0;
+  const unsigned row_m = (unsigned)ym * g.ld + x0;
+  const unsigned row_p = (unsigned)yp * g.ld + x0;
+  const unsigned row_h = (unsigned)y * g.ld + xh;
 
   // weights (solve_3d.cu:451-460): alpha / (h*h), zeroed at the volume faces
   const float hx2 = __fdiv_rn(a.alpha, __fmul_rn(a.hx, a.hx));
@@ -139,14 +152,14 @@ __global__ void __launch_bounds__(128) sweep_kernel(const SweepArgs a) {
   Vec<VEC> Su_c, Sv_c, Sw_c, ph_c;  // current plane
   Vec<VEC> u_c, v_c, w_c, dv_c, dw_c;
   {
-    const long long o = (long long)mirror_idx(z_begin - 1, g.d) * g.ps + row_c + x0;
+    const unsigned o = (unsigned)mirror_idx(z_begin - 1, g.d) * ps + row_c;
     Su_p = addv<VEC>(ldv<VEC>(a.u + o), ldv<VEC>(a.du + o));
     Sv_p = addv<VEC>(ldv<VEC>(a.v + o), ldv<VEC>(a.dv + o));
     Sw_p = addv<VEC>(ldv<VEC>(a.w + o), ldv<VEC>(a.dw + o));
     ph_p = ldv<VEC>(a.phi + o);
   }
   {
-    const long long o = (long long)z_begin * g.ps + row_c + x0;
+    const unsigned o = (unsigned)z_begin * ps + row_c;
     u_c = ldv<VEC>(a.u + o);
     v_c = ldv<VEC>(a.v + o);
     w_c = ldv<VEC>(a.w + o);
@@ -159,10 +172,26 @@ __global__ void __launch_bounds__(128) sweep_kernel(const SweepArgs a) {
     ph_c = ldv<VEC>(a.phi + o);
   }
 
+#pragma unroll UNROLL
   for (int z = z_begin; z < z_end; ++z) {
-    const long long pl = (long long)z * g.ps;
+    const unsigned pl = (unsigned)z * ps;
+    if (a.pf > 0) {
+      const int zp1 = z + 1 + a.pf;  // stencil fields are consumed one plane ahead
+      if (zp1 < g.d) {
+        const unsigned o = (unsigned)zp1 * ps + row_c;
+        prefetch_l2(a.u + o); prefetch_l2(a.v + o); prefetch_l2(a.w + o);
+        prefetch_l2(a.du + o); prefetch_l2(a.dv + o); prefetch_l2(a.dw + o);
+        prefetch_l2(a.phi + o);
+      }
+      const int zp0 = z + a.pf;
+      if (zp0 < g.d) {
+        const unsigned o = (unsigned)zp0 * ps + row_c;
+        prefetch_l2(a.fx + o); prefetch_l2(a.fy + o); prefetch_l2(a.fz + o);
+        prefetch_l2(a.ft + o); prefetch_l2(a.ksi + o);
+      }
+    }
     // ---- next plane (reflect at the rear face) ------------------------------------------------
-    const long long on = (long long)mirror_idx(z + 1, g.d) * g.ps + row_c + x0;
+    const unsigned on = (unsigned)mirror_idx(z + 1, g.d) * ps + row_c;
     const Vec<VEC> u_n = ldv<VEC>(a.u + on);
     const Vec<VEC> v_n = ldv<VEC>(a.v + on);
     const Vec<VEC> w_n = ldv<VEC>(a.w + on);
@@ -174,15 +203,15 @@ __global__ void __launch_bounds__(128) sweep_kernel(const SweepArgs a) {
     const Vec<VEC> Sv_n = addv<VEC>(v_n, dv_n);
     const Vec<VEC> Sw_n = addv<VEC>(w_n, dw_n);
     // ---- centre-only fields of the current plane ----------------------------------------------
-    const long long oc = pl + row_c + x0;
+    const unsigned oc = pl + row_c;
     const Vec<VEC> fx = ldv<VEC>(a.fx + oc);
     const Vec<VEC> fy = ldv<VEC>(a.fy + oc);
     const Vec<VEC> fz = ldv<VEC>(a.fz + oc);
     const Vec<VEC> ft = ldv<VEC>(a.ft + oc);
     const Vec<VEC> ks = ldv<VEC>(a.ksi + oc);
     // ---- y neighbours of the current plane -----------------------------------------------------
-    const long long om = pl + row_m + x0;
-    const long long op = pl + row_p + x0;
+    const unsigned om = pl + row_m;
+    const unsigned op = pl + row_p;
     const Vec<VEC> Su_ym = addv<VEC>(ldv<VEC>(a.u + om), ldv<VEC>(a.du + om));
     const Vec<VEC> Sv_ym = addv<VEC>(ldv<VEC>(a.v + om), ldv<VEC>(a.dv + om));
     const Vec<VEC> Sw_ym = addv<VEC>(ldv<VEC>(a.w + om), ldv<VEC>(a.dw + om));
@@ -192,14 +221,13 @@ __global__ void __launch_bounds__(128) sweep_kernel(const SweepArgs a) {
     const Vec<VEC> Sw_yp = addv<VEC>(ldv<VEC>(a.w + op), ldv<VEC>(a.dw + op));
     const Vec<VEC> ph_yp = ldv<VEC>(a.phi + op);
     // ---- x halo (two lanes per warp) -------------------------------------------------------------
-    float hSu = 0.f, hSv = 0.f, hSw = 0.f, hph = 0.f;
-    if (halo_lane) {
-      const long long oh = pl + row_c + xh;
-      hSu = __fadd_rn(__ldg(a.u + oh), __ldg(a.du + oh));
-      hSv = __fadd_rn(__ldg(a.v + oh), __ldg(a.dv + oh));
-      hSw = __fadd_rn(__ldg(a.w + oh), __ldg(a.dw + oh));
-      hph = __ldg(a.phi + oh);
-    }
+    // every lane loads (no branch, so the loads are issued together with the batch above and cost
+    // one memory round trip per plane instead of two); only lanes 0 / 31 use the value
+    const unsigned oh = pl + row_h;
+    const float hSu = __fadd_rn(__ldg(a.u + oh), __ldg(a.du + oh));
+    const float hSv = __fadd_rn(__ldg(a.v + oh), __ldg(a.dv + oh));
+    const float hSw = __fadd_rn(__ldg(a.w + oh), __ldg(a.dw + oh));
+    const float hph = __ldg(a.phi + oh);
     Vec<VEC> Su_xm, Su_xp, Sv_xm, Sv_xp, Sw_xm, Sw_xp, ph_xm, ph_xp;
     x_neighbours<VEC>(Su_c, hSu, lane, x0, g.w, Su_xm, Su_xp);
     x_neighbours<VEC>(Sv_c, hSv, lane, x0, g.w, Sv_xm, Sv_xp);
@@ -297,7 +325,14 @@ static void pick_grid(const Dims& g, int vec, int rows_per_block, dim3& grid, di
   grid = dim3(gx, gy, (g.d + zchunk - 1) / zchunk);
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+
 static int pick_vec(const Dims& g) {
+  static const int forced = env_int("FLOW3D_SWEEP_VEC", 0);  // tuning knob (results are identical)
+  if (forced == 1 || forced == 2 || forced == 4) return forced;
   if (g.w >= 96) return 4;
   if (g.w >= 48) return 2;
   return 1;
@@ -307,13 +342,23 @@ int launch_sweep(const float* fx, const float* fy, const float* fz, const float*
                  const float* u, const float* v, const float* w, const float* du, const float* dv,
                  const float* dw, const float* phi, const float* ksi, Dims g, float hx, float hy,
                  float hz, float alpha, float* odu, float* odv, float* odw, cudaStream_t st) {
-  SweepArgs a{fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, odu, odv, odw, g, hx, hy, hz, alpha, 0};
+  SweepArgs a{fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, odu, odv, odw, g, hx, hy, hz, alpha, 0, 0};
   const int vec = pick_vec(g);
+  static const int pf = env_int("FLOW3D_SWEEP_PF", 2);
+  static const int rows = env_int("FLOW3D_SWEEP_ROWS", 4);
+  a.pf = pf;
   dim3 grid, block;
-  pick_grid(g, vec, 4, grid, block, a.zchunk);
-  if (vec == 4) sweep_kernel<4><<<grid, block, 0, st>>>(a);
-  else if (vec == 2) sweep_kernel<2><<<grid, block, 0, st>>>(a);
-  else sweep_kernel<1><<<grid, block, 0, st>>>(a);
+  pick_grid(g, vec, rows, grid, block, a.zchunk);
+  static const int unroll = env_int("FLOW3D_SWEEP_UNROLL", 1);
+  if (unroll == 3) {
+    if (vec == 4) sweep_kernel<4, 3><<<grid, block, 0, st>>>(a);
+    else if (vec == 2) sweep_kernel<2, 3><<<grid, block, 0, st>>>(a);
+    else sweep_kernel<1, 3><<<grid, block, 0, st>>>(a);
+  } else {
+    if (vec == 4) sweep_kernel<4, 1><<<grid, block, 0, st>>>(a);
+    else if (vec == 2) sweep_kernel<2, 1><<<grid, block, 0, st>>>(a);
+    else sweep_kernel<1, 1><<<grid, block, 0, st>>>(a);
+  }
   count_launch();
   return check_launch("sweep_kernel");
 }
@@ -337,60 +382,131 @@ __device__ __forceinline__ float cdiff(const float* __restrict__ f, const float*
   return __fdiv_rn(t, two_h);
 }
 
-__global__ void __launch_bounds__(256) phi_ksi_kernel(const PhiKsiArgs a) {
+// value of ((f[p]-f[m]) + df[p]) - df[m]) / (2h) from already-loaded neighbours
+__device__ __forceinline__ float cdiff_r(float fp, float fm, float dfp, float dfm, float two_h) {
+  return __fdiv_rn(__fsub_rn(__fadd_rn(__fsub_rn(fp, fm), dfp), dfm), two_h);
+}
+
+// Same structure as the sweep: one warp per row segment of 32*VEC voxels marching along z, the six
+// stencil fields (u,du,v,dv,w,dw) register-rotated in z, x neighbours by shuffle, y neighbours from
+// the adjacent rows through L1.
+template <int VEC>
+__global__ void __launch_bounds__(128) phi_ksi_kernel(const PhiKsiArgs a, int zchunk, int pf) {
   const Dims g = a.g;
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  const int z = blockIdx.z;
-  if (x >= g.w || y >= g.h) return;
-  const long long c = (long long)z * g.ps + (long long)y * g.ld + x;
-  const long long ixp = c - x + mirror_idx(x + 1, g.w), ixm = c - x + mirror_idx(x - 1, g.w);
-  const long long rowbase = (long long)z * g.ps + x;
-  const long long iyp = rowbase + (long long)mirror_idx(y + 1, g.h) * g.ld;
-  const long long iym = rowbase + (long long)mirror_idx(y - 1, g.h) * g.ld;
-  const long long colbase = (long long)y * g.ld + x;
-  const long long izp = colbase + (long long)mirror_idx(z + 1, g.d) * g.ps;
-  const long long izm = colbase + (long long)mirror_idx(z - 1, g.d) * g.ps;
-
+  if (y >= g.h) return;
+  const int x0_raw = (blockIdx.x * 32 + lane) * VEC;
+  const bool active = x0_raw < g.w;
+  const int x0 = active ? x0_raw : ((g.w - 1) / VEC) * VEC;
+  const int z_begin = blockIdx.z * zchunk;
+  const int z_end = min(g.d, z_begin + zchunk);
+  if (z_begin >= z_end) return;
+  const int xh = (lane == 0) ? mirror_idx(x0 - 1, g.w) : ((lane == 31) ? mirror_idx(x0 + VEC, g.w) : x0);
+  const unsigned ps = (unsigned)g.ps;
+  const unsigned row_c = (unsigned)y * g.ld + x0;
+  const unsigned row_m = (unsigned)mirror_idx(y - 1, g.h) * g.ld + x0;
+  const unsigned row_p = (unsigned)mirror_idx(y + 1, g.h) * g.ld + x0;
+  const unsigned row_h = (unsigned)y * g.ld + xh;
   const float thx = __fadd_rn(a.hx, a.hx), thy = __fadd_rn(a.hy, a.hy), thz = __fadd_rn(a.hz, a.hz);
-  const float dux = cdiff(a.u, a.du, ixp, ixm, thx);
-  const float duy = cdiff(a.u, a.du, iyp, iym, thy);
-  const float duz = cdiff(a.u, a.du, izp, izm, thz);
-  const float dvx = cdiff(a.v, a.dv, ixp, ixm, thx);
-  const float dvy = cdiff(a.v, a.dv, iyp, iym, thy);
-  const float dvz = cdiff(a.v, a.dv, izp, izm, thz);
-  const float dwx = cdiff(a.w, a.dw, ixp, ixm, thx);
-  const float dwy = cdiff(a.w, a.dw, iyp, iym, thy);
-  const float dwz = cdiff(a.w, a.dw, izp, izm, thz);
 
-  // solve_3d.cu:217-218 as contracted by nvcc: mul(duy,duy) first, then one fma per term
-  float acc = __fmul_rn(duy, duy);
-  acc = __fmaf_rn(dux, dux, acc);
-  acc = __fmaf_rn(duz, duz, acc);
-  acc = __fmaf_rn(dvx, dvx, acc);
-  acc = __fmaf_rn(dvy, dvy, acc);
-  acc = __fmaf_rn(dvz, dvz, acc);
-  acc = __fmaf_rn(dwx, dwx, acc);
-  acc = __fmaf_rn(dwy, dwy, acc);
-  acc = __fmaf_rn(dwz, dwz, acc);
-  acc = __fmaf_rn(a.eps_s, a.eps_s, acc);
-  const float sq = __fsqrt_rn(acc);
-  a.phi[c] = __frcp_rn(__fadd_rn(sq, sq));
+  const float* F[6] = {a.u, a.du, a.v, a.dv, a.w, a.dw};
+  Vec<VEC> prev[6], cur[6];
+  {
+    const unsigned op = (unsigned)mirror_idx(z_begin - 1, g.d) * ps + row_c;
+    const unsigned oc = (unsigned)z_begin * ps + row_c;
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+      prev[f] = ldv<VEC>(F[f] + op);
+      cur[f] = ldv<VEC>(F[f] + oc);
+    }
+  }
+  for (int z = z_begin; z < z_end; ++z) {
+    const unsigned pl = (unsigned)z * ps;
+    if (pf > 0) {
+      const int zp1 = z + 1 + pf;
+      if (zp1 < g.d) {
+        const unsigned o = (unsigned)zp1 * ps + row_c;
+#pragma unroll
+        for (int f = 0; f < 6; ++f) prefetch_l2(F[f] + o);
+      }
+      const int zp0 = z + pf;
+      if (zp0 < g.d) {
+        const unsigned o = (unsigned)zp0 * ps + row_c;
+        prefetch_l2(a.fx + o); prefetch_l2(a.fy + o); prefetch_l2(a.fz + o); prefetch_l2(a.ft + o);
+      }
+    }
+    const unsigned on = (unsigned)mirror_idx(z + 1, g.d) * ps + row_c;
+    const unsigned oc = pl + row_c, om = pl + row_m, op = pl + row_p;
+    Vec<VEC> next[6], ym[6], yp[6], xm[6], xp[6];
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+      next[f] = ldv<VEC>(F[f] + on);
+      ym[f] = ldv<VEC>(F[f] + om);
+      yp[f] = ldv<VEC>(F[f] + op);
+    }
+    const Vec<VEC> fx = ldv<VEC>(a.fx + oc), fy = ldv<VEC>(a.fy + oc), fz = ldv<VEC>(a.fz + oc),
+                   ft = ldv<VEC>(a.ft + oc);
+    float halo[6];
+    {
+      const unsigned oh = pl + row_h;
+#pragma unroll
+      for (int f = 0; f < 6; ++f) halo[f] = __ldg(F[f] + oh);
+    }
+#pragma unroll
+    for (int f = 0; f < 6; ++f) x_neighbours<VEC>(cur[f], halo[f], lane, x0, g.w, xm[f], xp[f]);
 
-  const float fx = __ldg(a.fx + c), fy = __ldg(a.fy + c), fz = __ldg(a.fz + c), ft = __ldg(a.ft + c);
-  const float J11 = __fmul_rn(fx, fx), J22 = __fmul_rn(fy, fy), J33 = __fmul_rn(fz, fz);
-  const float J12 = __fmul_rn(fx, fy), J13 = __fmul_rn(fx, fz), J23 = __fmul_rn(fy, fz);
-  const float J14 = __fmul_rn(fx, ft), J24 = __fmul_rn(fy, ft), J34 = __fmul_rn(fz, ft);
-  const float du = __ldg(a.du + c), dv = __ldg(a.dv + c), dw = __ldg(a.dw + c);
-  // solve_3d.cu:250-254, operation by operation (row 3 keeps J13*du as the rounded product)
-  const float r1 = __fadd_rn(J14, __fmaf_rn(J13, dw, __fmaf_rn(J11, du, __fmul_rn(J12, dv))));
-  const float r2 = __fadd_rn(J24, __fmaf_rn(J23, dw, __fmaf_rn(J12, du, __fmul_rn(J22, dv))));
-  const float r3 = __fadd_rn(J34, __fmaf_rn(J33, dw, __fmaf_rn(J23, dv, __fmul_rn(J13, du))));
-  const float r4 = __fmaf_rn(ft, ft, __fmaf_rn(J34, dw, __fmaf_rn(J14, du, __fmul_rn(J24, dv))));
-  float s = __fadd_rn(__fmaf_rn(dw, r3, __fmaf_rn(du, r1, __fmul_rn(dv, r2))), r4);
-  s = __fmul_rn(s, (s > 0.f) ? 1.f : 0.f);
-  const float sq2 = __fsqrt_rn(__fmaf_rn(a.eps_d, a.eps_d, s));
-  a.ksi[c] = __frcp_rn(__fadd_rn(sq2, sq2));
+    Vec<VEC> ophi, oksi;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float dux = cdiff_r(xp[0].v[i], xm[0].v[i], xp[1].v[i], xm[1].v[i], thx);
+      const float duy = cdiff_r(yp[0].v[i], ym[0].v[i], yp[1].v[i], ym[1].v[i], thy);
+      const float duz = cdiff_r(next[0].v[i], prev[0].v[i], next[1].v[i], prev[1].v[i], thz);
+      const float dvx = cdiff_r(xp[2].v[i], xm[2].v[i], xp[3].v[i], xm[3].v[i], thx);
+      const float dvy = cdiff_r(yp[2].v[i], ym[2].v[i], yp[3].v[i], ym[3].v[i], thy);
+      const float dvz = cdiff_r(next[2].v[i], prev[2].v[i], next[3].v[i], prev[3].v[i], thz);
+      const float dwx = cdiff_r(xp[4].v[i], xm[4].v[i], xp[5].v[i], xm[5].v[i], thx);
+      const float dwy = cdiff_r(yp[4].v[i], ym[4].v[i], yp[5].v[i], ym[5].v[i], thy);
+      const float dwz = cdiff_r(next[4].v[i], prev[4].v[i], next[5].v[i], prev[5].v[i], thz);
+      // solve_3d.cu:217-218 as contracted by nvcc: mul(duy,duy) first, then one fma per term
+      float acc = __fmul_rn(duy, duy);
+      acc = __fmaf_rn(dux, dux, acc);
+      acc = __fmaf_rn(duz, duz, acc);
+      acc = __fmaf_rn(dvx, dvx, acc);
+      acc = __fmaf_rn(dvy, dvy, acc);
+      acc = __fmaf_rn(dvz, dvz, acc);
+      acc = __fmaf_rn(dwx, dwx, acc);
+      acc = __fmaf_rn(dwy, dwy, acc);
+      acc = __fmaf_rn(dwz, dwz, acc);
+      acc = __fmaf_rn(a.eps_s, a.eps_s, acc);
+      const float sq = __fsqrt_rn(acc);
+      ophi.v[i] = __frcp_rn(__fadd_rn(sq, sq));
+
+      const float gx = fx.v[i], gy = fy.v[i], gz = fz.v[i], gt = ft.v[i];
+      const float J11 = __fmul_rn(gx, gx), J22 = __fmul_rn(gy, gy), J33 = __fmul_rn(gz, gz);
+      const float J12 = __fmul_rn(gx, gy), J13 = __fmul_rn(gx, gz), J23 = __fmul_rn(gy, gz);
+      const float J14 = __fmul_rn(gx, gt), J24 = __fmul_rn(gy, gt), J34 = __fmul_rn(gz, gt);
+      const float du = cur[1].v[i], dv = cur[3].v[i], dw = cur[5].v[i];
+      // solve_3d.cu:250-254, operation by operation (row 3 keeps J13*du as the rounded product)
+      const float r1 = __fadd_rn(J14, __fmaf_rn(J13, dw, __fmaf_rn(J11, du, __fmul_rn(J12, dv))));
+      const float r2 = __fadd_rn(J24, __fmaf_rn(J23, dw, __fmaf_rn(J12, du, __fmul_rn(J22, dv))));
+      const float r3 = __fadd_rn(J34, __fmaf_rn(J33, dw, __fmaf_rn(J23, dv, __fmul_rn(J13, du))));
+      const float r4 = __fmaf_rn(gt, gt, __fmaf_rn(J34, dw, __fmaf_rn(J14, du, __fmul_rn(J24, dv))));
+      float sv = __fadd_rn(__fmaf_rn(dw, r3, __fmaf_rn(du, r1, __fmul_rn(dv, r2))), r4);
+      sv = __fmul_rn(sv, (sv > 0.f) ? 1.f : 0.f);
+      const float sq2 = __fsqrt_rn(__fmaf_rn(a.eps_d, a.eps_d, sv));
+      oksi.v[i] = __frcp_rn(__fadd_rn(sq2, sq2));
+    }
+    if (active) {
+      stv<VEC>(a.phi + oc, ophi);
+      stv<VEC>(a.ksi + oc, oksi);
+    }
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+      prev[f] = cur[f];
+      cur[f] = next[f];
+    }
+  }
 }
 
 int launch_phi_ksi(const float* fx, const float* fy, const float* fz, const float* ft,
@@ -398,9 +514,16 @@ int launch_phi_ksi(const float* fx, const float* fy, const float* fz, const floa
                    const float* dv, const float* dw, Dims g, float hx, float hy, float hz,
                    float eps_s, float eps_d, float* phi, float* ksi, cudaStream_t st) {
   PhiKsiArgs a{fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, g, hx, hy, hz, eps_s, eps_d};
-  dim3 block(32, 8, 1);
-  dim3 grid((g.w + 31) / 32, (g.h + 7) / 8, g.d);
-  phi_ksi_kernel<<<grid, block, 0, st>>>(a);
+  static const int forced = env_int("FLOW3D_PHIKSI_VEC", 0);
+  static const int pf = env_int("FLOW3D_PHIKSI_PF", 2);
+  int vec = (g.w >= 48) ? 2 : 1;  // measured: VEC=2 (114 regs, 16 warps/SM) beats VEC=4 (191 regs)
+  if (forced == 1 || forced == 2 || forced == 4) vec = forced;
+  dim3 grid, block;
+  int zchunk = 0;
+  pick_grid(g, vec, 4, grid, block, zchunk);
+  if (vec == 4) phi_ksi_kernel<4><<<grid, block, 0, st>>>(a, zchunk, pf);
+  else if (vec == 2) phi_ksi_kernel<2><<<grid, block, 0, st>>>(a, zchunk, pf);
+  else phi_ksi_kernel<1><<<grid, block, 0, st>>>(a, zchunk, pf);
   count_launch();
   return check_launch("phi_ksi_kernel");
 }
