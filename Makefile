@@ -15,7 +15,7 @@ CU_OBJS   := $(CU_SRCS:.cu=.o)
 HOST_SRCS := $(wildcard $(PKG)/host/*.cpp)
 HOST_OBJS := $(HOST_SRCS:.cpp=.o)
 
-all: $(LIB) oracle
+all: $(LIB) oracle apps
 
 $(CSRC)/kernels_median.o: $(CSRC)/median_net_27.inc $(CSRC)/median_net_125.inc
 
@@ -34,11 +34,18 @@ $(LIB): $(CU_OBJS) $(HOST_OBJS)
 oracle:
 	$(MAKE) -C oracle liboracle.so
 
+# example programs against the reference-shaped C++ host API
+APPS := build/flow3d_cli build/example_main
+apps: $(APPS)
+build/%: apps/%.cpp $(LIB)
+	@mkdir -p build
+	$(HOSTCXX) -std=c++17 -O2 -Iinclude $< -o $@ -L$(PKG) -lflow3d_b200 -Wl,-rpath,'$$ORIGIN/../$(PKG)'
+
 ref:
 	bash oracle/build_ref.sh
 
 clean:
-	rm -f $(CU_OBJS) $(HOST_OBJS) $(CSRC)/*.ptxas.log $(LIB)
+	rm -f $(CU_OBJS) $(HOST_OBJS) $(CSRC)/*.ptxas.log $(LIB) $(APPS)
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle ref clean
+.PHONY: all oracle ref clean apps

@@ -68,6 +68,9 @@ SIGNATURES = {
     "flow3d_upload": (C.c_int, [_vp, _vp, _sz3, C.c_size_t, _vp]),
     "flow3d_download": (C.c_int, [_vp, _vp, _sz3, C.c_size_t, _vp]),
     "flow3d_stream_synchronize": (C.c_int, [_vp]),
+    "flow3d_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
+    "flow3d_host_free": (C.c_int, [_vp]),
+    "flow3d_device_name": (C.c_int, [C.c_int, C.c_char_p, C.c_size_t]),
     "flow3d_gauss_blur": (C.c_int, [_vp, _vp, _vp, _sz3, C.c_size_t, C.c_float, _vp]),
     "flow3d_resample": (C.c_int, [_vp, _sz3, C.c_size_t, _vp, _sz3, C.c_size_t, _vp, _vp, _vp]),
     "flow3d_warp": (C.c_int, [_vp] * 5 + [_sz3, C.c_size_t, _f3, _vp, _vp]),

@@ -449,6 +449,27 @@ int flow3d_stream_synchronize(void* stream) {
   return FLOW3D_OK;
 }
 
+int flow3d_host_alloc(void** host_ptr, size_t bytes) {
+  if (!host_ptr) return FLOW3D_ERR_INVALID_ARG;
+  *host_ptr = nullptr;
+  if (flow3d_device_count() <= 0) return FLOW3D_ERR_NO_DEVICE;
+  F3D_CUDA(cudaHostAlloc(host_ptr, bytes, cudaHostAllocDefault));
+  return FLOW3D_OK;
+}
+int flow3d_host_free(void* host_ptr) {
+  if (!host_ptr) return FLOW3D_OK;
+  F3D_CUDA(cudaFreeHost(host_ptr));
+  return FLOW3D_OK;
+}
+int flow3d_device_name(int device, char* buf, size_t n) {
+  if (!buf || n == 0) return FLOW3D_ERR_INVALID_ARG;
+  if (flow3d_device_count() <= 0) return FLOW3D_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  F3D_CUDA(cudaGetDeviceProperties(&prop, device));
+  std::snprintf(buf, n, "%s", prop.name);
+  return FLOW3D_OK;
+}
+
 // ---- stage wrappers ----------------------------------------------------------------------------
 int flow3d_gauss_blur(const float* in, float* out, float* tmp, const size_t dims[3], size_t ld,
                       float sigma, void* stream) {

@@ -82,6 +82,12 @@ int flow3d_memset(void* dev_ptr, int value, size_t bytes, void* stream);
 int flow3d_upload(const float* host, float* dev, const size_t dims[3], size_t ld, void* stream);
 int flow3d_download(const float* dev, float* host, const size_t dims[3], size_t ld, void* stream);
 int flow3d_stream_synchronize(void* stream);
+/* page-locked host memory for fast asynchronous H2D/D2H (FLOW3D_ERR_NO_DEVICE without a device;
+ * the reference has the same option behind ALLOCATE_PINNED_MEMORY, src/data_types/data3d.cpp:28-60) */
+int flow3d_host_alloc(void** host_ptr, size_t bytes);
+int flow3d_host_free(void* host_ptr);
+/* name of a device into buf (NUL-terminated, truncated to n) */
+int flow3d_device_name(int device, char* buf, size_t n);
 
 /* ---- stage functions (device pointers) ----------------------------------------------------- */
 

@@ -1,0 +1,67 @@
+"""The C++ host API that mirrors the reference's classes (include/flow3d/*.h): built into
+libflow3d_b200.so and exercised through the two example programs."""
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+CLI = os.path.join(ROOT, "build", "flow3d_cli")
+EXAMPLE = os.path.join(ROOT, "build", "example_main")
+META = json.load(open(os.path.join(GOLDEN, "reference_flows.json")))
+
+
+def test_cli_usage_and_loud_failure_without_device(lib, tmp_path):
+    assert os.path.exists(CLI), "build/flow3d_cli missing: run make"
+    r = subprocess.run([CLI], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage:" in r.stdout
+    if lib.flow3d_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    a = np.zeros((8, 8, 8), np.uint8)
+    a.tofile(tmp_path / "a.raw")
+    r = subprocess.run([CLI, "--dims", "8", "8", "8", "--frame0", str(tmp_path / "a.raw"), "--frame1",
+                        str(tmp_path / "a.raw")], capture_output=True, text=True)
+    assert r.returncode == 1 and "no cuda capable devices" in r.stdout.lower()
+
+
+@pytest.mark.gpu
+def test_example_main_reproduces_reference_flow(pair_128, tmp_path):
+    """the reference's driver sequence (src/main.cpp:150-185) compiled against our headers"""
+    f0, f1 = pair_128
+    f0.astype(np.uint8).tofile(tmp_path / "f0.raw")
+    f1.astype(np.uint8).tofile(tmp_path / "f1.raw")
+    r = subprocess.run([EXAMPLE, str(tmp_path / "f0.raw"), str(tmp_path / "f1.raw"), "128", "128", "128", str(tmp_path)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Total GPU computation time" in r.stdout
+    for c in "uvw":
+        got = np.fromfile(tmp_path / ("flow-%s-128-128-128.raw" % c), np.float32)
+        assert hashlib.sha256(got.tobytes()).hexdigest() == META["pair128"]["full_sha256"][c]
+
+
+@pytest.mark.gpu
+def test_cli_f32_vtk_and_params(tmp_path):
+    rng = np.random.default_rng(3)
+    a = (rng.random((12, 20, 28)) * 255).astype(np.float32)
+    b = np.roll(a, 1, axis=2)
+    a.tofile(tmp_path / "a.raw")
+    b.tofile(tmp_path / "b.raw")
+    r = subprocess.run([CLI, "--dims", "28", "20", "12", "--frame0", str(tmp_path / "a.raw"), "--frame1",
+                        str(tmp_path / "b.raw"), "--f32", "--out", str(tmp_path / "o"), "--vtk", str(tmp_path / "o.vtk"),
+                        "--param", "outer_iterations_count=2", "--param", "warp_levels_count=3", "--reps", "2"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("FLOW3D_SOLVE") == 2
+    u = np.fromfile(tmp_path / "o_u.raw", np.float32)
+    assert u.size == 12 * 20 * 28 and np.isfinite(u).all()
+    vtk = open(tmp_path / "o.vtk", "rb").read()
+    assert vtk.startswith(b"# vtk DataFile Version 2.0\n3D Vector field computed by GpuFlow3D\nBINARY\n")
+    assert b"DIMENSIONS 28 20 12\n" in vtk and len(vtk) > 3 * 4 * u.size
+    # wrong size is an error (data3d.cpp:124-131)
+    r = subprocess.run([CLI, "--dims", "28", "20", "13", "--frame0", str(tmp_path / "a.raw"), "--frame1",
+                        str(tmp_path / "b.raw"), "--f32"], capture_output=True, text=True)
+    assert r.returncode == 2 and "wrong dimensions" in r.stdout
