@@ -42,6 +42,12 @@ class Params(C.Structure):
     ]
 
 
+class ZSlab(C.Structure):
+    """flow3d_zslab: z-slab view of a level sharded along z (include/flow3d_c.h)."""
+    _fields_ = [("z0_global", C.c_size_t), ("depth_global", C.c_size_t), ("z_begin", C.c_size_t),
+                ("z_end", C.c_size_t)]
+
+
 LEVEL_CALLBACK = C.CFUNCTYPE(None, C.c_int, C.POINTER(C.c_size_t), C.c_size_t, C.c_void_p, C.c_void_p,
                              C.c_void_p, C.c_void_p)
 
@@ -82,6 +88,14 @@ SIGNATURES = {
                                                   C.c_float, C.c_float, C.c_float, _vp]),
     "flow3d_add3": (C.c_int, [_vp] * 6 + [_sz3, C.c_size_t, _vp]),
     "flow3d_median": (C.c_int, [_vp, _vp, _sz3, C.c_size_t, C.c_size_t, _vp]),
+    "flow3d_sweep_slab": (C.c_int, [_vp] * 12 + [_sz3, C.c_size_t, C.POINTER(ZSlab), _f3, C.c_float] + [_vp] * 4),
+    "flow3d_phi_ksi_slab": (C.c_int, [_vp] * 10 + [_sz3, C.c_size_t, C.POINTER(ZSlab), _f3, C.c_float, C.c_float] + [_vp] * 3),
+    "flow3d_warp_derivatives_slab": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp, _vp, _vp, _sz3, C.c_size_t,
+                                               C.POINTER(ZSlab), _f3] + [_vp] * 5),
+    "flow3d_median_slab": (C.c_int, [_vp, _vp, _sz3, C.c_size_t, C.POINTER(ZSlab), C.c_size_t, _vp]),
+    "flow3d_resample_slab": (C.c_int, [_vp, _sz3, C.c_size_t, C.POINTER(ZSlab), _vp, _sz3, C.c_size_t, C.POINTER(ZSlab),
+                                       _vp, _vp, _vp]),
+    "flow3d_absmax": (C.c_int, [_vp, _sz3, C.c_size_t, _vp, _vp]),
     "flow3d_solver_workspace_bytes": (C.c_size_t, [C.c_size_t] * 3),
     "flow3d_solver_create": (C.c_int, [C.c_size_t] * 3 + [C.c_int, C.POINTER(_vp)]),
     "flow3d_solver_destroy": (C.c_int, [_vp]),

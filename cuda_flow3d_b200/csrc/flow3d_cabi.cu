@@ -138,16 +138,21 @@ static int gauss_blur(const float* in, float* out, float* tmp, Dims g, float sig
 
 static inline size_t aligned_ld(size_t w) { return (w + 3) & ~(size_t)3; }
 
-// X -> Y -> Z (cuda_operation_resample.cpp:95-105) through two scratch volumes
+// X -> Y -> Z (cuda_operation_resample.cpp:95-105) through two scratch volumes.  With slabs, id[2] /
+// od[2] are local depths; x and y passes run on every local input plane, the z pass on the output range.
 static int resample(const float* in, const size_t id[3], size_t in_ld, float* out, const size_t od[3],
-                    size_t out_ld, float* ta, float* tb, cudaStream_t st) {
+                    size_t out_ld, float* ta, float* tb, cudaStream_t st,
+                    const flow3d_zslab* in_slab = nullptr, const flow3d_zslab* out_slab = nullptr) {
   size_t d0[3] = {id[0], id[1], id[2]};
   size_t d1[3] = {od[0], id[1], id[2]};
   size_t d2[3] = {od[0], od[1], id[2]};
   const size_t l1 = aligned_ld(od[0]);
-  F3D_TRY(launch_resample_axis(in, make_dims(d0, in_ld), ta, make_dims(d1, l1), 0, st));
-  F3D_TRY(launch_resample_axis(ta, make_dims(d1, l1), tb, make_dims(d2, l1), 1, st));
-  F3D_TRY(launch_resample_axis(tb, make_dims(d2, l1), out, make_dims(od, out_ld), 2, st));
+  const Dims g0 = make_slab_dims(d0, in_ld, in_slab), g1 = make_slab_dims(d1, l1, in_slab),
+             g2 = make_slab_dims(d2, l1, in_slab), g3 = make_slab_dims(od, out_ld, out_slab);
+  const ZRange all_in{0, (int)id[2]};
+  F3D_TRY(launch_resample_axis(in, g0, ta, g1, 0, all_in, st));
+  F3D_TRY(launch_resample_axis(ta, g1, tb, g2, 1, all_in, st));
+  F3D_TRY(launch_resample_axis(tb, g2, out, g3, 2, make_range(g3, out_slab), st));
   return FLOW3D_OK;
 }
 
@@ -166,12 +171,12 @@ static int solve_level(const float* fx, const float* fy, const float* fz, const 
   float *a0 = du, *a1 = dv, *a2 = dw, *b0 = tdu, *b1 = tdv, *b2 = tdw;
   for (size_t i = 0; i < outer; ++i) {  // :194-257
     if (tm) tm->mark(FLOW3D_STAGE_PHI_KSI, st, nvox);
-    F3D_TRY(launch_phi_ksi(fx, fy, fz, ft, u, v, w, a0, a1, a2, g, h[0], h[1], h[2], eps_s, eps_d, phi,
-                           ksi, st));
+    F3D_TRY(launch_phi_ksi(fx, fy, fz, ft, u, v, w, a0, a1, a2, g, ZRange{0, g.d}, h[0], h[1], h[2], eps_s,
+                           eps_d, phi, ksi, st));
     if (tm) tm->mark(FLOW3D_STAGE_SWEEP, st, nvox * (double)inner);
     for (size_t j = 0; j < inner; ++j) {
-      F3D_TRY(launch_sweep(fx, fy, fz, ft, u, v, w, a0, a1, a2, phi, ksi, g, h[0], h[1], h[2], alpha,
-                           b0, b1, b2, st));
+      F3D_TRY(launch_sweep(fx, fy, fz, ft, u, v, w, a0, a1, a2, phi, ksi, g, ZRange{0, g.d}, h[0], h[1], h[2],
+                           alpha, b0, b1, b2, st));
       std::swap(a0, b0);
       std::swap(a1, b1);
       std::swap(a2, b2);
@@ -284,7 +289,8 @@ static int run_pyramid(flow3d_solver* s, const float* in0, const float* in1, siz
     }
     // :348-369 warp, fused with the derivative stencils the solver kernels would recompute
     tm->mark(FLOW3D_STAGE_WARP, st, nvox);
-    F3D_TRY(launch_warp_derivatives(pf0, pf1, u, v, w, g, h[0], h[1], h[2], fx, fy, fz, ft, st));
+    F3D_TRY(launch_warp_derivatives(pf0, pf1, 0, g.d, u, v, w, g, ZRange{0, g.d}, h[0], h[1], h[2], fx, fy, fz,
+                                    ft, st));
     // :372-417
     F3D_TRY(solve_level(fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, tdu, tdv, tdw, g, h,
                         p->outer_iterations_count, p->inner_iterations_count, p->equation_alpha,
@@ -299,12 +305,13 @@ static int run_pyramid(flow3d_solver* s, const float* in0, const float* in1, siz
     tm->mark(FLOW3D_STAGE_MEDIAN, st, 3.0 * nvox);
     {
       size_t r = p->median_radius;
-      int rc = launch_median(u, tdu, g, (int)r, st);
+      const ZRange all{0, g.d};
+      int rc = launch_median(u, tdu, g, all, (int)r, st);
       if (rc == FLOW3D_OK) {
         std::swap(u, tdu);
-        F3D_TRY(launch_median(v, tdu, g, (int)r, st));
+        F3D_TRY(launch_median(v, tdu, g, all, (int)r, st));
         std::swap(v, tdu);
-        F3D_TRY(launch_median(w, tdu, g, (int)r, st));
+        F3D_TRY(launch_median(w, tdu, g, all, (int)r, st));
         std::swap(w, tdu);
       } else if (rc != FLOW3D_ERR_UNSUPPORTED) {
         return rc;
@@ -511,7 +518,8 @@ int flow3d_warp_derivatives(const float* f0, const float* f1, const float* u, co
   const void* ps[] = {f0, f1, u, v, w, fx, fy, fz, ft};
   for (const void* p : ps) F3D_TRY(check_volume(p, dims, ld));
   if (!h) return FLOW3D_ERR_INVALID_ARG;
-  return launch_warp_derivatives(f0, f1, u, v, w, make_dims(dims, ld), h[0], h[1], h[2], fx, fy, fz, ft,
+  const Dims g = make_dims(dims, ld);
+  return launch_warp_derivatives(f0, f1, 0, g.d, u, v, w, g, ZRange{0, g.d}, h[0], h[1], h[2], fx, fy, fz, ft,
                                  S(stream));
 }
 
@@ -523,8 +531,9 @@ int flow3d_phi_ksi(const float* fx, const float* fy, const float* fz, const floa
   const void* ps[] = {fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi};
   for (const void* p : ps) F3D_TRY(check_volume(p, dims, ld));
   if (!h) return FLOW3D_ERR_INVALID_ARG;
-  return launch_phi_ksi(fx, fy, fz, ft, u, v, w, du, dv, dw, make_dims(dims, ld), h[0], h[1], h[2],
-                        eps_smooth, eps_data, phi, ksi, S(stream));
+  const Dims g = make_dims(dims, ld);
+  return launch_phi_ksi(fx, fy, fz, ft, u, v, w, du, dv, dw, g, ZRange{0, g.d}, h[0], h[1], h[2], eps_smooth,
+                        eps_data, phi, ksi, S(stream));
 }
 
 int flow3d_sweep(const float* fx, const float* fy, const float* fz, const float* ft,
@@ -535,8 +544,9 @@ int flow3d_sweep(const float* fx, const float* fy, const float* fz, const float*
   const void* ps[] = {fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, du_out, dv_out, dw_out};
   for (const void* p : ps) F3D_TRY(check_volume(p, dims, ld));
   if (!h || du_out == du || dv_out == dv || dw_out == dw) return FLOW3D_ERR_INVALID_ARG;
-  return launch_sweep(fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, make_dims(dims, ld), h[0], h[1],
-                      h[2], alpha, du_out, dv_out, dw_out, S(stream));
+  const Dims g = make_dims(dims, ld);
+  return launch_sweep(fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, g, ZRange{0, g.d}, h[0], h[1], h[2], alpha,
+                      du_out, dv_out, dw_out, S(stream));
 }
 
 int flow3d_solve_level(const float* fx, const float* fy, const float* fz, const float* ft,
@@ -566,7 +576,80 @@ int flow3d_median(const float* in, float* out, const size_t dims[3], size_t ld, 
   F3D_TRY(check_volume(in, dims, ld));
   F3D_TRY(check_volume(out, dims, ld));
   if (in == out || radius == 0 || radius > 64) return FLOW3D_ERR_INVALID_ARG;
-  return launch_median(in, out, make_dims(dims, ld), (int)radius, S(stream));
+  const Dims g = make_dims(dims, ld);
+  return launch_median(in, out, g, ZRange{0, g.d}, (int)radius, S(stream));
+}
+
+// ---- z-slab variants -------------------------------------------------------------------------------
+int flow3d_sweep_slab(const float* fx, const float* fy, const float* fz, const float* ft,
+                      const float* u, const float* v, const float* w, const float* du,
+                      const float* dv, const float* dw, const float* phi, const float* ksi,
+                      const size_t dims[3], size_t ld, const flow3d_zslab* slab, const float h[3],
+                      float alpha, float* du_out, float* dv_out, float* dw_out, void* stream) {
+  const void* ps[] = {fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, du_out, dv_out, dw_out};
+  for (const void* p : ps) F3D_TRY(check_volume(p, dims, ld));
+  F3D_TRY(check_slab(dims, slab));
+  if (!h || du_out == du || dv_out == dv || dw_out == dw) return FLOW3D_ERR_INVALID_ARG;
+  const Dims g = make_slab_dims(dims, ld, slab);
+  return launch_sweep(fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, g, make_range(g, slab), h[0], h[1], h[2],
+                      alpha, du_out, dv_out, dw_out, S(stream));
+}
+
+int flow3d_phi_ksi_slab(const float* fx, const float* fy, const float* fz, const float* ft,
+                        const float* u, const float* v, const float* w, const float* du,
+                        const float* dv, const float* dw, const size_t dims[3], size_t ld,
+                        const flow3d_zslab* slab, const float h[3], float eps_smooth, float eps_data,
+                        float* phi, float* ksi, void* stream) {
+  const void* ps[] = {fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi};
+  for (const void* p : ps) F3D_TRY(check_volume(p, dims, ld));
+  F3D_TRY(check_slab(dims, slab));
+  if (!h) return FLOW3D_ERR_INVALID_ARG;
+  const Dims g = make_slab_dims(dims, ld, slab);
+  return launch_phi_ksi(fx, fy, fz, ft, u, v, w, du, dv, dw, g, make_range(g, slab), h[0], h[1], h[2],
+                        eps_smooth, eps_data, phi, ksi, S(stream));
+}
+
+int flow3d_warp_derivatives_slab(const float* f0, const float* f1, size_t f1_z0_global,
+                                 size_t f1_depth_local, const float* u, const float* v,
+                                 const float* w, const size_t dims[3], size_t ld,
+                                 const flow3d_zslab* slab, const float h[3], float* fx, float* fy,
+                                 float* fz, float* ft, void* stream) {
+  const void* ps[] = {f0, u, v, w, fx, fy, fz, ft};
+  for (const void* p : ps) F3D_TRY(check_volume(p, dims, ld));
+  F3D_TRY(check_slab(dims, slab));
+  if (!h || !f1 || !aligned16(f1) || f1_depth_local == 0) return FLOW3D_ERR_INVALID_ARG;
+  const Dims g = make_slab_dims(dims, ld, slab);
+  if (f1_z0_global + f1_depth_local > (size_t)g.dg) return FLOW3D_ERR_INVALID_ARG;
+  return launch_warp_derivatives(f0, f1, (int)f1_z0_global, (int)f1_depth_local, u, v, w, g, make_range(g, slab),
+                                 h[0], h[1], h[2], fx, fy, fz, ft, S(stream));
+}
+
+int flow3d_median_slab(const float* in, float* out, const size_t dims[3], size_t ld,
+                       const flow3d_zslab* slab, size_t radius, void* stream) {
+  F3D_TRY(check_volume(in, dims, ld));
+  F3D_TRY(check_volume(out, dims, ld));
+  F3D_TRY(check_slab(dims, slab));
+  if (in == out || radius == 0 || radius > 64) return FLOW3D_ERR_INVALID_ARG;
+  const Dims g = make_slab_dims(dims, ld, slab);
+  return launch_median(in, out, g, make_range(g, slab), (int)radius, S(stream));
+}
+
+int flow3d_resample_slab(const float* in, const size_t in_dims[3], size_t in_ld,
+                         const flow3d_zslab* in_slab, float* out, const size_t out_dims[3],
+                         size_t out_ld, const flow3d_zslab* out_slab, float* tmp_a, float* tmp_b,
+                         void* stream) {
+  F3D_TRY(check_volume(in, in_dims, in_ld));
+  F3D_TRY(check_volume(out, out_dims, out_ld));
+  F3D_TRY(check_slab(in_dims, in_slab));
+  F3D_TRY(check_slab(out_dims, out_slab));
+  if (!tmp_a || !tmp_b || !aligned16(tmp_a) || !aligned16(tmp_b) || in == out) return FLOW3D_ERR_INVALID_ARG;
+  return resample(in, in_dims, in_ld, out, out_dims, out_ld, tmp_a, tmp_b, S(stream), in_slab, out_slab);
+}
+
+int flow3d_absmax(const float* dev, const size_t dims[3], size_t ld, float* out_dev, void* stream) {
+  F3D_TRY(check_volume(dev, dims, ld));
+  if (!out_dev) return FLOW3D_ERR_INVALID_ARG;
+  return launch_absmax(dev, make_dims(dims, ld), out_dev, S(stream));
 }
 
 // ---- solver ----------------------------------------------------------------------------------------

@@ -57,14 +57,15 @@ int launch_conv_axis(const float* in, float* out, Dims g, const float* taps_host
 // ------------------------------------------------------------------------------------------------
 template <int AXIS>
 __global__ void __launch_bounds__(256) resample_axis_kernel(const float* __restrict__ in, Dims gi,
-                                                            float* __restrict__ out, Dims go) {
+                                                            float* __restrict__ out, Dims go, int zs) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  const int z = blockIdx.z;
+  const int z = zs + blockIdx.z;  // local output plane
   if (x >= go.w || y >= go.h) return;
-  const unsigned o = AXIS == 0 ? x : (AXIS == 1 ? y : z);
-  const unsigned long long a = AXIS == 0 ? gi.w : (AXIS == 1 ? gi.h : gi.d);
-  const unsigned long long b = AXIS == 0 ? go.w : (AXIS == 1 ? go.h : go.d);
+  // along z the tap arithmetic runs in GLOBAL plane indices (slabs: z0g/dg), then maps to local
+  const unsigned o = AXIS == 0 ? x : (AXIS == 1 ? y : (go.z0g + z));
+  const unsigned long long a = AXIS == 0 ? gi.w : (AXIS == 1 ? gi.h : gi.dg);
+  const unsigned long long b = AXIS == 0 ? go.w : (AXIS == 1 ? go.h : go.dg);
   const float fa = (float)a, fb = (float)b;
   const float delta = __fdiv_rn(fa, fb);
   const float norm = __fdiv_rn(fb, fa);
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(256) resample_axis_kernel(const float* __restr
   // input element (left_i + j) along AXIS, same other coordinates
   const long long base = AXIS == 0 ? ((long long)z * gi.ps + (long long)y * gi.ld + left_i)
                        : AXIS == 1 ? ((long long)z * gi.ps + (long long)left_i * gi.ld + x)
-                                   : ((long long)left_i * gi.ps + (long long)y * gi.ld + x);
+                                   : ((long long)(left_i - gi.z0g) * gi.ps + (long long)y * gi.ld + x);
   const long long stride = AXIS == 0 ? 1 : (AXIS == 1 ? (long long)gi.ld : gi.ps);
   const float first = __fsub_rn((float)(left_i + 1), left_f);
   float value = 0.f;
@@ -90,13 +91,14 @@ __global__ void __launch_bounds__(256) resample_axis_kernel(const float* __restr
   out[(long long)z * go.ps + (long long)y * go.ld + x] = __fmul_rn(norm, value);
 }
 
-int launch_resample_axis(const float* in, Dims gin, float* out, Dims gout, int axis,
+int launch_resample_axis(const float* in, Dims gin, float* out, Dims gout, int axis, ZRange zr,
                          cudaStream_t st) {
+  if (zr.end <= zr.begin) return FLOW3D_OK;
   dim3 block(32, 8, 1);
-  dim3 grid((gout.w + 31) / 32, (gout.h + 7) / 8, gout.d);
-  if (axis == 0) resample_axis_kernel<0><<<grid, block, 0, st>>>(in, gin, out, gout);
-  else if (axis == 1) resample_axis_kernel<1><<<grid, block, 0, st>>>(in, gin, out, gout);
-  else resample_axis_kernel<2><<<grid, block, 0, st>>>(in, gin, out, gout);
+  dim3 grid((gout.w + 31) / 32, (gout.h + 7) / 8, zr.end - zr.begin);
+  if (axis == 0) resample_axis_kernel<0><<<grid, block, 0, st>>>(in, gin, out, gout, zr.begin);
+  else if (axis == 1) resample_axis_kernel<1><<<grid, block, 0, st>>>(in, gin, out, gout, zr.begin);
+  else resample_axis_kernel<2><<<grid, block, 0, st>>>(in, gin, out, gout, zr.begin);
   count_launch();
   return check_launch("resample_axis_kernel");
 }

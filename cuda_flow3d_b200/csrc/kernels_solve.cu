@@ -85,6 +85,7 @@ struct SweepArgs {
   float hx, hy, hz, alpha;
   int zchunk;
   int pf;  // prefetch distance in planes (0 = off)
+  int zs, ze;  // compute range (local planes)
 };
 
 // x-neighbour values of a VEC-wide register group: left[i] / right[i] are the values at x-1 / x+1
@@ -122,8 +123,8 @@ __global__ void __launch_bounds__(128) sweep_kernel(const SweepArgs a) {
   const int x0_raw = (blockIdx.x * 32 + lane) * VEC;
   const bool active = x0_raw < g.w;
   const int x0 = active ? x0_raw : ((g.w - 1) / VEC) * VEC;  // idle lanes shadow the last group
-  const int z_begin = blockIdx.z * a.zchunk;
-  const int z_end = min(g.d, z_begin + a.zchunk);
+  const int z_begin = a.zs + blockIdx.z * a.zchunk;
+  const int z_end = min(a.ze, z_begin + a.zchunk);
   if (z_begin >= z_end) return;
 
   const int ym = mirror_idx(y - 1, g.h);
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(128) sweep_kernel(const SweepArgs a) {
   Vec<VEC> Su_c, Sv_c, Sw_c, ph_c;  // current plane
   Vec<VEC> u_c, v_c, w_c, dv_c, dw_c;
   {
-    const unsigned o = (unsigned)mirror_idx(z_begin - 1, g.d) * ps + row_c;
+    const unsigned o = (unsigned)z_neighbour(g, z_begin, -1) * ps + row_c;
     Su_p = addv<VEC>(ldv<VEC>(a.u + o), ldv<VEC>(a.du + o));
     Sv_p = addv<VEC>(ldv<VEC>(a.v + o), ldv<VEC>(a.dv + o));
     Sw_p = addv<VEC>(ldv<VEC>(a.w + o), ldv<VEC>(a.dw + o));
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(128) sweep_kernel(const SweepArgs a) {
       }
     }
     // ---- next plane (reflect at the rear face) ------------------------------------------------
-    const unsigned on = (unsigned)mirror_idx(z + 1, g.d) * ps + row_c;
+    const unsigned on = (unsigned)z_neighbour(g, z, 1) * ps + row_c;
     const Vec<VEC> u_n = ldv<VEC>(a.u + on);
     const Vec<VEC> v_n = ldv<VEC>(a.v + on);
     const Vec<VEC> w_n = ldv<VEC>(a.w + on);
@@ -234,8 +235,9 @@ __global__ void __launch_bounds__(128) sweep_kernel(const SweepArgs a) {
     x_neighbours<VEC>(Sw_c, hSw, lane, x0, g.w, Sw_xm, Sw_xp);
     x_neighbours<VEC>(ph_c, hph, lane, x0, g.w, ph_xm, ph_xp);
 
-    const float wzp = (z < g.d - 1) ? hz2 : 0.f;
-    const float wzm = (z > 0) ? hz2 : 0.f;
+    const int zg = g.z0g + z;  // faces are the GLOBAL ones when the level is sharded
+    const float wzp = (zg < g.dg - 1) ? hz2 : 0.f;
+    const float wzm = (zg > 0) ? hz2 : 0.f;
 
     Vec<VEC> rdu, rdv, rdw;
 #pragma unroll
@@ -308,7 +310,8 @@ __global__ void __launch_bounds__(128) sweep_kernel(const SweepArgs a) {
   }
 }
 
-static void pick_grid(const Dims& g, int vec, int rows_per_block, dim3& grid, dim3& block, int& zchunk) {
+static void pick_grid(const Dims& g, ZRange zr, int vec, int rows_per_block, dim3& grid, dim3& block, int& zchunk) {
+  const int nz = zr.end - zr.begin;
   block = dim3(32, rows_per_block, 1);
   const int gx = (g.w + 32 * vec - 1) / (32 * vec);
   const int gy = (g.h + rows_per_block - 1) / rows_per_block;
@@ -318,11 +321,12 @@ static void pick_grid(const Dims& g, int vec, int rows_per_block, dim3& grid, di
   const long long want = (long long)sm_count() * 16;
   long long nchunks = (want + per_plane - 1) / per_plane;
   if (nchunks < 1) nchunks = 1;
-  long long len = (g.d + nchunks - 1) / nchunks;
+  long long len = (nz + nchunks - 1) / nchunks;
   if (len < 8) len = 8;
-  if (len > g.d) len = g.d;
+  if (len > nz) len = nz;
+  if (len < 1) len = 1;
   zchunk = (int)len;
-  grid = dim3(gx, gy, (g.d + zchunk - 1) / zchunk);
+  grid = dim3(gx, gy, (nz + zchunk - 1) / zchunk);
 }
 
 static int env_int(const char* name, int dflt) {
@@ -340,15 +344,17 @@ static int pick_vec(const Dims& g) {
 
 int launch_sweep(const float* fx, const float* fy, const float* fz, const float* ft,
                  const float* u, const float* v, const float* w, const float* du, const float* dv,
-                 const float* dw, const float* phi, const float* ksi, Dims g, float hx, float hy,
-                 float hz, float alpha, float* odu, float* odv, float* odw, cudaStream_t st) {
-  SweepArgs a{fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, odu, odv, odw, g, hx, hy, hz, alpha, 0, 0};
+                 const float* dw, const float* phi, const float* ksi, Dims g, ZRange zr, float hx,
+                 float hy, float hz, float alpha, float* odu, float* odv, float* odw, cudaStream_t st) {
+  if (zr.end <= zr.begin) return FLOW3D_OK;
+  SweepArgs a{fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, odu, odv, odw, g, hx, hy, hz, alpha, 0, 0,
+              zr.begin, zr.end};
   const int vec = pick_vec(g);
   static const int pf = env_int("FLOW3D_SWEEP_PF", 2);
   static const int rows = env_int("FLOW3D_SWEEP_ROWS", 4);
   a.pf = pf;
   dim3 grid, block;
-  pick_grid(g, vec, rows, grid, block, a.zchunk);
+  pick_grid(g, zr, vec, rows, grid, block, a.zchunk);
   static const int unroll = env_int("FLOW3D_SWEEP_UNROLL", 1);
   if (unroll == 3) {
     if (vec == 4) sweep_kernel<4, 3><<<grid, block, 0, st>>>(a);
@@ -391,7 +397,7 @@ __device__ __forceinline__ float cdiff_r(float fp, float fm, float dfp, float df
 // stencil fields (u,du,v,dv,w,dw) register-rotated in z, x neighbours by shuffle, y neighbours from
 // the adjacent rows through L1.
 template <int VEC>
-__global__ void __launch_bounds__(128) phi_ksi_kernel(const PhiKsiArgs a, int zchunk, int pf) {
+__global__ void __launch_bounds__(128) phi_ksi_kernel(const PhiKsiArgs a, int zchunk, int pf, int zs, int ze) {
   const Dims g = a.g;
   const int lane = threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -399,8 +405,8 @@ __global__ void __launch_bounds__(128) phi_ksi_kernel(const PhiKsiArgs a, int zc
   const int x0_raw = (blockIdx.x * 32 + lane) * VEC;
   const bool active = x0_raw < g.w;
   const int x0 = active ? x0_raw : ((g.w - 1) / VEC) * VEC;
-  const int z_begin = blockIdx.z * zchunk;
-  const int z_end = min(g.d, z_begin + zchunk);
+  const int z_begin = zs + blockIdx.z * zchunk;
+  const int z_end = min(ze, z_begin + zchunk);
   if (z_begin >= z_end) return;
   const int xh = (lane == 0) ? mirror_idx(x0 - 1, g.w) : ((lane == 31) ? mirror_idx(x0 + VEC, g.w) : x0);
   const unsigned ps = (unsigned)g.ps;
@@ -413,7 +419,7 @@ __global__ void __launch_bounds__(128) phi_ksi_kernel(const PhiKsiArgs a, int zc
   const float* F[6] = {a.u, a.du, a.v, a.dv, a.w, a.dw};
   Vec<VEC> prev[6], cur[6];
   {
-    const unsigned op = (unsigned)mirror_idx(z_begin - 1, g.d) * ps + row_c;
+    const unsigned op = (unsigned)z_neighbour(g, z_begin, -1) * ps + row_c;
     const unsigned oc = (unsigned)z_begin * ps + row_c;
 #pragma unroll
     for (int f = 0; f < 6; ++f) {
@@ -436,7 +442,7 @@ __global__ void __launch_bounds__(128) phi_ksi_kernel(const PhiKsiArgs a, int zc
         prefetch_l2(a.fx + o); prefetch_l2(a.fy + o); prefetch_l2(a.fz + o); prefetch_l2(a.ft + o);
       }
     }
-    const unsigned on = (unsigned)mirror_idx(z + 1, g.d) * ps + row_c;
+    const unsigned on = (unsigned)z_neighbour(g, z, 1) * ps + row_c;
     const unsigned oc = pl + row_c, om = pl + row_m, op = pl + row_p;
     Vec<VEC> next[6], ym[6], yp[6], xm[6], xp[6];
 #pragma unroll
@@ -511,8 +517,9 @@ __global__ void __launch_bounds__(128) phi_ksi_kernel(const PhiKsiArgs a, int zc
 
 int launch_phi_ksi(const float* fx, const float* fy, const float* fz, const float* ft,
                    const float* u, const float* v, const float* w, const float* du,
-                   const float* dv, const float* dw, Dims g, float hx, float hy, float hz,
+                   const float* dv, const float* dw, Dims g, ZRange zr, float hx, float hy, float hz,
                    float eps_s, float eps_d, float* phi, float* ksi, cudaStream_t st) {
+  if (zr.end <= zr.begin) return FLOW3D_OK;
   PhiKsiArgs a{fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, g, hx, hy, hz, eps_s, eps_d};
   static const int forced = env_int("FLOW3D_PHIKSI_VEC", 0);
   static const int pf = env_int("FLOW3D_PHIKSI_PF", 2);
@@ -520,10 +527,10 @@ int launch_phi_ksi(const float* fx, const float* fy, const float* fz, const floa
   if (forced == 1 || forced == 2 || forced == 4) vec = forced;
   dim3 grid, block;
   int zchunk = 0;
-  pick_grid(g, vec, 4, grid, block, zchunk);
-  if (vec == 4) phi_ksi_kernel<4><<<grid, block, 0, st>>>(a, zchunk, pf);
-  else if (vec == 2) phi_ksi_kernel<2><<<grid, block, 0, st>>>(a, zchunk, pf);
-  else phi_ksi_kernel<1><<<grid, block, 0, st>>>(a, zchunk, pf);
+  pick_grid(g, zr, vec, 4, grid, block, zchunk);
+  if (vec == 4) phi_ksi_kernel<4><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end);
+  else if (vec == 2) phi_ksi_kernel<2><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end);
+  else phi_ksi_kernel<1><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end);
   count_launch();
   return check_launch("phi_ksi_kernel");
 }
@@ -557,6 +564,39 @@ int launch_add3(float* u, float* v, float* w, const float* du, const float* dv, 
   add3_kernel<<<(unsigned)grid, block, 0, st>>>(u, v, w, du, dv, dw, n4);
   count_launch();
   return check_launch("add3_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// max |x| (used to size the frame-1 halo of a z-sharded warp): warp shuffles + one atomicMax on the
+// non-negative float's integer image
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ in, Dims g,
+                                                     unsigned* __restrict__ out) {
+  float m = 0.f;
+  const long long rows = (long long)g.h * g.d;
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float* row = in + r * g.ld;
+    for (int x = threadIdx.x; x < g.w; x += blockDim.x) {
+      const float v = fabsf(__ldg(row + x));
+      m = (v > m || v != v) ? v : m;  // NaN sticks (largest bit pattern in the atomicMax below)
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float t = __shfl_xor_sync(0xffffffffu, m, o);
+    m = (t > m || t != t) ? t : m;
+  }
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
+int launch_absmax(const float* in, Dims g, float* out, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float), st);
+  if (e != cudaSuccess) { note_cuda_error(e, "cudaMemsetAsync"); return FLOW3D_ERR_CUDA; }
+  long long rows = (long long)g.h * g.d;
+  long long blocks = rows < (long long)sm_count() * 16 ? rows : (long long)sm_count() * 16;
+  absmax_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, g, reinterpret_cast<unsigned*>(out));
+  count_launch();
+  return check_launch("absmax_kernel");
 }
 
 }  // namespace f3d

@@ -8,7 +8,8 @@ namespace f3d {
 struct WarpGeom {
   Dims g;
   float rhx, rhy, rhz;  // rcp.rn(h): the reference evaluates (1.f / h) with a correctly rounded rcp
-  float wmax, hmax, dmax;  // (float)(dim - 1)
+  float wmax, hmax, dmax;  // (float)(dim - 1), dmax from the GLOBAL depth
+  int f1_z0g, f1_d;        // frame 1 may live in its own (taller) z-slab
 };
 
 // Warped frame-1 value at voxel (x,y,z): trilinear sample of f1 at x + u/h, or f0 when the target
@@ -22,7 +23,7 @@ __device__ __forceinline__ float warp_at(const float* __restrict__ f0, const flo
   const long long c = (long long)z * g.ps + (long long)y * g.ld + x;
   const float x_f = __fmaf_rn(q.rhx, __ldg(u + c), (float)(unsigned)x);
   const float y_f = __fmaf_rn(q.rhy, __ldg(v + c), (float)(unsigned)y);
-  const float z_f = __fmaf_rn(q.rhz, __ldg(w + c), (float)(unsigned)z);
+  const float z_f = __fmaf_rn(q.rhz, __ldg(w + c), (float)(unsigned)(g.z0g + z));  // global plane
   if ((x_f < 0.f) || (x_f > q.wmax) || (y_f < 0.f) || (y_f > q.hmax) || (z_f < 0.f) ||
       (z_f > q.dmax) || isnan(x_f) || isnan(y_f) || isnan(z_f)) {
     return __ldg(f0 + c);
@@ -34,16 +35,20 @@ __device__ __forceinline__ float warp_at(const float* __restrict__ f0, const flo
   const float dz = __fsub_rn(z_f, (float)zi);
   const int x1 = min(g.w - 1, xi + 1);
   const int y1 = min(g.h - 1, yi + 1);
-  const int z1 = min(g.d - 1, zi + 1);
+  const int z1g = min(g.dg - 1, zi + 1);
+  // global -> local plane of the frame-1 slab; clamped so that an under-sized slab can never fault
+  // (the caller sizes the slab from max|w|, see cuda_flow3d_b200/dist.py)
+  const int z0l = min(max(zi - q.f1_z0g, 0), q.f1_d - 1);
+  const int z1l = min(max(z1g - q.f1_z0g, 0), q.f1_d - 1);
   const float ox = __fsub_rn(1.f, dx), oy = __fsub_rn(1.f, dy);
   const float w00 = __fmul_rn(ox, oy);
   const float w10 = __fmul_rn(dx, oy);
   const float w01 = __fmul_rn(ox, dy);
   const float w11 = __fmul_rn(dx, dy);
-  const long long r00 = (long long)zi * g.ps + (long long)yi * g.ld;
-  const long long r01 = (long long)zi * g.ps + (long long)y1 * g.ld;
-  const long long r10 = (long long)z1 * g.ps + (long long)yi * g.ld;
-  const long long r11 = (long long)z1 * g.ps + (long long)y1 * g.ld;
+  const long long r00 = (long long)z0l * g.ps + (long long)yi * g.ld;
+  const long long r01 = (long long)z0l * g.ps + (long long)y1 * g.ld;
+  const long long r10 = (long long)z1l * g.ps + (long long)yi * g.ld;
+  const long long r11 = (long long)z1l * g.ps + (long long)y1 * g.ld;
   float v0 = __fmul_rn(w10, __ldg(f1 + r00 + x1));
   v0 = __fmaf_rn(w00, __ldg(f1 + r00 + xi), v0);
   v0 = __fmaf_rn(w01, __ldg(f1 + r01 + xi), v0);
@@ -55,15 +60,17 @@ __device__ __forceinline__ float warp_at(const float* __restrict__ f0, const flo
   return __fmaf_rn(__fsub_rn(1.f, dz), v0, __fmul_rn(dz, v1));
 }
 
-static WarpGeom make_geom(Dims g, float hx, float hy, float hz) {
+static WarpGeom make_geom(Dims g, float hx, float hy, float hz, int f1_z0g = 0, int f1_d = -1) {
   WarpGeom q;
   q.g = g;
+  q.f1_z0g = f1_z0g;
+  q.f1_d = f1_d < 0 ? g.d : f1_d;
   q.rhx = 1.f / hx;  // IEEE division of 1 == rcp.rn
   q.rhy = 1.f / hy;
   q.rhz = 1.f / hz;
   q.wmax = (float)(g.w - 1);
   q.hmax = (float)(g.h - 1);
-  q.dmax = (float)(g.d - 1);
+  q.dmax = (float)(g.dg - 1);
   return q;
 }
 
@@ -111,8 +118,8 @@ __global__ void __launch_bounds__(256) derivatives_kernel(const float* __restric
   const long long iyp = rb + (long long)mirror_idx(y + 1, g.h) * g.ld;
   const long long iym = rb + (long long)mirror_idx(y - 1, g.h) * g.ld;
   const long long cb = (long long)y * g.ld + x;
-  const long long izp = cb + (long long)mirror_idx(z + 1, g.d) * g.ps;
-  const long long izm = cb + (long long)mirror_idx(z - 1, g.d) * g.ps;
+  const long long izp = cb + (long long)z_neighbour(g, z, 1) * g.ps;
+  const long long izm = cb + (long long)z_neighbour(g, z, -1) * g.ps;
   fx[c] = deriv(__ldg(f0 + ixp), __ldg(f0 + ixm), __ldg(f1w + ixp), __ldg(f1w + ixm), __fmul_rn(hx, 4.f));
   fy[c] = deriv(__ldg(f0 + iyp), __ldg(f0 + iym), __ldg(f1w + iyp), __ldg(f1w + iym), __fmul_rn(hy, 4.f));
   fz[c] = deriv(__ldg(f0 + izp), __ldg(f0 + izm), __ldg(f1w + izp), __ldg(f1w + izm), __fmul_rn(hz, 4.f));
@@ -136,7 +143,7 @@ int launch_derivatives(const float* f0, const float* f1w, Dims g, float hx, floa
 __global__ void __launch_bounds__(WD_TX* WD_TY) warp_derivatives_kernel(
     const float* __restrict__ f0, const float* __restrict__ f1, const float* __restrict__ u,
     const float* __restrict__ v, const float* __restrict__ w, WarpGeom q, float hx, float hy,
-    float hz, int zchunk, float* __restrict__ fx, float* __restrict__ fy, float* __restrict__ fz,
+    float hz, int zchunk, int zs, int ze, float* __restrict__ fx, float* __restrict__ fy, float* __restrict__ fz,
     float* __restrict__ ft) {
   const Dims& g = q.g;
   __shared__ float sw[3][WD_TY + 2][WD_TX + 2];  // ring of warped planes
@@ -144,8 +151,8 @@ __global__ void __launch_bounds__(WD_TX* WD_TY) warp_derivatives_kernel(
   const int tid = ty * WD_TX + tx;
   const int bx = blockIdx.x * WD_TX, by = blockIdx.y * WD_TY;
   const int x = bx + tx, y = by + ty;
-  const int z_begin = blockIdx.z * zchunk;
-  const int z_end = min(g.d, z_begin + zchunk);
+  const int z_begin = zs + blockIdx.z * zchunk;
+  const int z_end = min(ze, z_begin + zchunk);
   if (z_begin >= z_end) return;
   const bool valid = (x < g.w) && (y < g.h);
   const float fhx = __fmul_rn(hx, 4.f), fhy = __fmul_rn(hy, 4.f), fhz = __fmul_rn(hz, 4.f);
@@ -153,8 +160,8 @@ __global__ void __launch_bounds__(WD_TX* WD_TY) warp_derivatives_kernel(
 
   // fill ring slot `slot` with the warped plane mirror(zz): cell (r,cx) <-> voxel
   // (mirror(bx-1+cx), mirror(by-1+r)) -- mirrored coordinates reproduce the reference's halo.
-  auto fill = [&](int slot, int zz) {
-    const int zs = mirror_idx(zz, g.d);
+  auto fill = [&](int slot, int zz) {  // zz = local plane index, possibly one beyond a global face
+    const int zs = z_neighbour(g, zz, 0);
     for (int i = tid; i < CELLS; i += WD_TX * WD_TY) {
       const int r = i / (WD_TX + 2), cx = i - r * (WD_TX + 2);
       const int gx = mirror_idx(bx - 1 + cx, g.w), gy = mirror_idx(by - 1 + r, g.h);
@@ -174,8 +181,8 @@ __global__ void __launch_bounds__(WD_TX* WD_TY) warp_derivatives_kernel(
       const long long iyp = rb + (long long)mirror_idx(y + 1, g.h) * g.ld;
       const long long iym = rb + (long long)mirror_idx(y - 1, g.h) * g.ld;
       const long long cb = (long long)y * g.ld + x;
-      const long long izp = cb + (long long)mirror_idx(z + 1, g.d) * g.ps;
-      const long long izm = cb + (long long)mirror_idx(z - 1, g.d) * g.ps;
+      const long long izp = cb + (long long)z_neighbour(g, z, 1) * g.ps;
+      const long long izm = cb + (long long)z_neighbour(g, z, -1) * g.ps;
       const float wc = sw[sc][ty + 1][tx + 1];
       fx[c] = deriv(__ldg(f0 + ixp), __ldg(f0 + ixm), sw[sc][ty + 1][tx + 2], sw[sc][ty + 1][tx], fhx);
       fy[c] = deriv(__ldg(f0 + iyp), __ldg(f0 + iym), sw[sc][ty + 2][tx + 1], sw[sc][ty][tx + 1], fhy);
@@ -187,20 +194,22 @@ __global__ void __launch_bounds__(WD_TX* WD_TY) warp_derivatives_kernel(
   }
 }
 
-int launch_warp_derivatives(const float* f0, const float* f1, const float* u, const float* v,
-                            const float* w, Dims g, float hx, float hy, float hz, float* fx,
-                            float* fy, float* fz, float* ft, cudaStream_t st) {
+int launch_warp_derivatives(const float* f0, const float* f1, int f1_z0g, int f1_d, const float* u,
+                            const float* v, const float* w, Dims g, ZRange zr, float hx, float hy,
+                            float hz, float* fx, float* fy, float* fz, float* ft, cudaStream_t st) {
+  if (zr.end <= zr.begin) return FLOW3D_OK;
+  const int nz = zr.end - zr.begin;
   dim3 block(WD_TX, WD_TY, 1);
   const int gx = (g.w + WD_TX - 1) / WD_TX, gy = (g.h + WD_TY - 1) / WD_TY;
   const long long per_plane = (long long)gx * gy;
   long long nchunks = ((long long)sm_count() * 8 + per_plane - 1) / per_plane;
   if (nchunks < 1) nchunks = 1;
-  long long len = (g.d + nchunks - 1) / nchunks;
+  long long len = (nz + nchunks - 1) / nchunks;
   if (len < 8) len = 8;
-  if (len > g.d) len = g.d;
-  dim3 grid(gx, gy, (unsigned)((g.d + len - 1) / len));
-  warp_derivatives_kernel<<<grid, block, 0, st>>>(f0, f1, u, v, w, make_geom(g, hx, hy, hz), hx, hy,
-                                                   hz, (int)len, fx, fy, fz, ft);
+  if (len > nz) len = nz;
+  dim3 grid(gx, gy, (unsigned)((nz + len - 1) / len));
+  warp_derivatives_kernel<<<grid, block, 0, st>>>(f0, f1, u, v, w, make_geom(g, hx, hy, hz, f1_z0g, f1_d),
+                                                   hx, hy, hz, (int)len, zr.begin, zr.end, fx, fy, fz, ft);
   count_launch();
   return check_launch("warp_derivatives_kernel");
 }

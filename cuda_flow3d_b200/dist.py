@@ -1,0 +1,399 @@
+"""z-sharded multi-GPU flow solve: one process per GPU, `torch.distributed` for the plumbing.
+
+Decomposition (the reference's own precedent is the z-slab + halo scheme of its
+out-of-core path, src/cuda_operations/partial_data/cuda_operation_solve_p.cpp:358-417):
+
+* every level with enough planes is split along z: rank g owns planes [a, b) = [g*d/G, (g+1)*d/G) and
+  keeps a buffer [A, B) = [a-H, b+H) (clipped at the global faces) with H = inner_iterations + 1 ghost
+  planes per side;
+* the solver is point-Jacobi, so with an H-deep ghost zone the phi/ksi update plus all
+  `inner` sweeps of one outer iteration run WITHOUT communication on shrinking ranges (phi on
+  [A+1,B-1), sweep j on [A+1+j, B-1-j)); one neighbour exchange of H planes of (du,dv,dw) per outer
+  iteration restores the ghosts.  The result is bit-identical to the single-GPU solve;
+* the blurred full-resolution frames are replicated on every rank (each rank gets both input frames),
+  so per-level frames are resampled locally for exactly the planes a rank needs -- including the
+  data-dependent z reach of the warp (max|w|/hz planes, from an on-device max reduction);
+* the flow is exchanged only between z neighbours: H ghost planes after the prolongation, and the
+  per-outer-iteration exchange above; the 5^3 median and the next prolongation read ghosts that are
+  already valid.  No collective sits on the data path;
+* coarse levels (too few planes to shard) are computed redundantly by every rank (replicas): no
+  communication, and every rank holds the full flow when the first sharded level starts.
+
+The compute backend is the C ABI (`CabiBackend`, CUDA tensors, NCCL).  `OracleBackend` (CPU tensors,
+gloo) plugs the test oracle's slab functions into the same orchestration so that the partitioning /
+exchange logic is covered by world_size-2 tests on CPU; it is test infrastructure and is only
+instantiated by tests/.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import ZSlab, check, f3, load, sz3
+from .api import DEFAULTS
+
+
+def own_range(d, rank, world):
+    return (rank * d) // world, ((rank + 1) * d) // world
+
+
+def f32(x):
+    return np.float32(x)
+
+
+def source_range(o_lo, o_hi, a, b):
+    """input planes [lo, hi) read by output planes [o_lo, o_hi) of an axis resampled from a to b samples
+    (same float arithmetic as the kernels: resample_3d.cu:41-48)"""
+    delta = f32(a) / f32(b)
+    lo = int(np.floor(f32(o_lo) * delta))
+    hi = int(min(f32(a), np.ceil(f32(o_hi) * delta)))
+    return max(lo, 0), min(hi, a)
+
+
+class Slab:
+    """a z-slab of one field of one level: tensor (dl, h, ld) holding global planes [A, A+dl)"""
+
+    def __init__(self, t, A, dg, w):
+        self.t, self.A, self.dg, self.w = t, int(A), int(dg), int(w)
+
+    @property
+    def dl(self):
+        return self.t.shape[0]
+
+    @property
+    def B(self):
+        return self.A + self.t.shape[0]
+
+    def planes(self, g_lo, g_hi):
+        return self.t[g_lo - self.A:g_hi - self.A]
+
+
+# =====================================================================================================
+class CabiBackend:
+    """stage functions of libflow3d_b200.so on CUDA tensors (current torch stream)"""
+    name = "cabi"
+
+    def __init__(self, device):
+        self.L = load()
+        self.dev = torch.device("cuda", device)
+        torch.cuda.set_device(self.dev)
+        check(self.L.flow3d_set_device(device), "set_device")
+
+    def _sp(self):
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def ld(self, w):
+        return int(self.L.flow3d_aligned_ld(w))
+
+    def empty(self, w, h, dl):
+        return torch.empty((dl, h, self.ld(w)), dtype=torch.float32, device=self.dev)
+
+    def zeros(self, w, h, dl):
+        return torch.zeros((dl, h, self.ld(w)), dtype=torch.float32, device=self.dev)
+
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(t.data_ptr())
+
+    def _slab(self, s, lo, hi):
+        return ZSlab(s.A, s.dg, lo - s.A, hi - s.A)
+
+    def blur(self, full, sigma):
+        d, h, ld = full.shape
+        out, tmp = torch.empty_like(full), torch.empty_like(full)
+        check(self.L.flow3d_gauss_blur(self._p(full), self._p(out), self._p(tmp), sz3((self.w_full, h, d)), ld, sigma,
+                                       self._sp()), "blur")
+        return out
+
+    def resample(self, src, src_whd_global, out_whd_global, out_A, out_lo, out_hi, out=None):
+        """src: Slab of the input level; returns/fills a Slab of the output level with plane 0 = out_A,
+        computing global output planes [out_lo, out_hi)"""
+        iw, ih, idg = src_whd_global
+        ow, oh, odg = out_whd_global
+        if out is None:
+            raise ValueError("out slab required")
+        tmp_a = torch.empty((src.dl, ih, self.ld(ow)), dtype=torch.float32, device=self.dev)
+        tmp_b = torch.empty((src.dl, oh, self.ld(ow)), dtype=torch.float32, device=self.dev)
+        in_slab = ZSlab(src.A, idg, 0, src.dl)
+        out_slab = ZSlab(out.A, odg, out_lo - out.A, out_hi - out.A)
+        check(self.L.flow3d_resample_slab(self._p(src.t), sz3((iw, ih, src.dl)), src.t.shape[2], C.byref(in_slab),
+                                          self._p(out.t), sz3((ow, oh, out.dl)), out.t.shape[2], C.byref(out_slab),
+                                          self._p(tmp_a), self._p(tmp_b), self._sp()), "resample_slab")
+        return out
+
+    def warp_terms(self, f0, f1, u, v, w, h, lo, hi):
+        """image terms on global planes [lo, hi): (fx, fy, fz, ft) slabs (same geometry as u)"""
+        terms = [torch.empty_like(u.t) for _ in range(4)]
+        dims = sz3((u.w, u.t.shape[1], u.dl))
+        sl = self._slab(u, lo, hi)
+        check(self.L.flow3d_warp_derivatives_slab(self._p(f0.t), self._p(f1.t), f1.A, f1.dl, self._p(u.t), self._p(v.t),
+                                                  self._p(w.t), dims, u.t.shape[2], C.byref(sl), f3(h),
+                                                  *[self._p(t) for t in terms], self._sp()), "warp_derivatives_slab")
+        return terms
+
+    def phi_ksi(self, terms, u, v, w, du, dv, dw, h, eps_s, eps_d, phi, ksi, lo, hi):
+        dims = sz3((u.w, u.t.shape[1], u.dl))
+        sl = self._slab(u, lo, hi)
+        check(self.L.flow3d_phi_ksi_slab(*[self._p(t) for t in terms], self._p(u.t), self._p(v.t), self._p(w.t),
+                                         self._p(du), self._p(dv), self._p(dw), dims, u.t.shape[2], C.byref(sl), f3(h),
+                                         eps_s, eps_d, self._p(phi), self._p(ksi), self._sp()), "phi_ksi_slab")
+
+    def sweep(self, terms, u, v, w, d_in, phi, ksi, h, alpha, d_out, lo, hi):
+        dims = sz3((u.w, u.t.shape[1], u.dl))
+        sl = self._slab(u, lo, hi)
+        check(self.L.flow3d_sweep_slab(*[self._p(t) for t in terms], self._p(u.t), self._p(v.t), self._p(w.t),
+                                       *[self._p(t) for t in d_in], self._p(phi), self._p(ksi), dims, u.t.shape[2],
+                                       C.byref(sl), f3(h), alpha, *[self._p(t) for t in d_out], self._sp()),
+              "sweep_slab")
+
+    def add3(self, flow, d):
+        u = flow[0]
+        check(self.L.flow3d_add3(self._p(flow[0].t), self._p(flow[1].t), self._p(flow[2].t), self._p(d[0]),
+                                 self._p(d[1]), self._p(d[2]), sz3((u.w, u.t.shape[1], u.dl)), u.t.shape[2], self._sp()),
+              "add3")
+
+    def median(self, src, dst_t, radius, lo, hi):
+        dims = sz3((src.w, src.t.shape[1], src.dl))
+        sl = self._slab(src, lo, hi)
+        check(self.L.flow3d_median_slab(self._p(src.t), self._p(dst_t), dims, src.t.shape[2], C.byref(sl), radius,
+                                        self._sp()), "median_slab")
+
+    def absmax(self, s):
+        out = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        check(self.L.flow3d_absmax(self._p(s.t), sz3((s.w, s.t.shape[1], s.dl)), s.t.shape[2], self._p(out),
+                                   self._sp()), "absmax")
+        return float(out.item())
+
+    def from_numpy_full(self, a):
+        """tight numpy (D,H,W) -> padded device tensor (D,H,ld)"""
+        d, h, w = a.shape
+        t = self.zeros(w, h, d)
+        t[:, :, :w] = torch.from_numpy(np.ascontiguousarray(a)).to(self.dev)
+        self.w_full = w
+        return t
+
+    def to_numpy(self, t, w):
+        return t[:, :, :w].contiguous().cpu().numpy()
+
+
+class OracleBackend:
+    """the CPU test oracle's slab functions behind the same interface (gloo tests only)"""
+    name = "oracle"
+
+    def __init__(self, oracle):
+        self.o = oracle
+        self.dev = torch.device("cpu")
+        import ctypes as C_
+        L = oracle.lib
+        f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+        lg, sz, fl = C_.c_long, C_.c_size_t, C_.c_float
+        L.o_warp_slab.argtypes = [f32p, f32p, lg, f32p, f32p, f32p, sz, sz, sz, lg, lg, lg, fl, fl, fl, f32p]
+        L.o_phi_ksi_slab.argtypes = [f32p] * 8 + [sz, sz, lg, lg, lg, lg] + [fl] * 5 + [f32p] * 2
+        L.o_sweep_slab.argtypes = [f32p] * 10 + [sz, sz, lg, lg, lg, lg] + [fl] * 4 + [f32p] * 3
+        L.o_median_slab.argtypes = [f32p, f32p, sz, sz, lg, lg, lg, lg, sz]
+        L.o_median_slab.restype = C_.c_int
+        L.o_resample_z_slab.argtypes = [f32p, sz, sz, lg, lg, f32p, lg, lg, lg, lg]
+
+    def ld(self, w):
+        return w
+
+    def empty(self, w, h, dl):
+        return torch.empty((dl, h, w), dtype=torch.float32)
+
+    def zeros(self, w, h, dl):
+        return torch.zeros((dl, h, w), dtype=torch.float32)
+
+    def blur(self, full, sigma):
+        return torch.from_numpy(self.o.gauss_blur(full.numpy(), sigma))
+
+    def resample(self, src, src_whd_global, out_whd_global, out_A, out_lo, out_hi, out=None):
+        iw, ih, idg = src_whd_global
+        ow, oh, odg = out_whd_global
+        a = src.t.numpy()
+        t1 = self.o.resample_axis(a, ow, 0)
+        t2 = self.o.resample_axis(t1, oh, 1)
+        self.o.lib.o_resample_z_slab(t2, ow, oh, src.A, idg, out.t.numpy(), out.A, odg, out_lo - out.A, out_hi - out.A)
+        return out
+
+    def warp_terms(self, f0, f1, u, v, w, h, lo, hi):
+        # the oracle recomputes the derivatives inside phi/ksi and the sweep from (f0, warped f1), which
+        # need the warped frame one plane beyond [lo, hi): warp the whole buffer
+        out = torch.zeros_like(u.t)
+        dl, hh, ww = u.t.shape
+        self.o.lib.o_warp_slab(f0.t.numpy(), f1.t.numpy(), f1.A, u.t.numpy(), v.t.numpy(), w.t.numpy(), ww, hh, u.dg,
+                               u.A, 0, dl, h[0], h[1], h[2], out.numpy())
+        return (f0.t, out)
+
+    def phi_ksi(self, terms, u, v, w, du, dv, dw, h, eps_s, eps_d, phi, ksi, lo, hi):
+        dl, hh, ww = u.t.shape
+        self.o.lib.o_phi_ksi_slab(terms[0].numpy(), terms[1].numpy(), u.t.numpy(), v.t.numpy(), w.t.numpy(), du.numpy(),
+                                  dv.numpy(), dw.numpy(), ww, hh, u.A, u.dg, lo - u.A, hi - u.A, h[0], h[1], h[2], eps_s,
+                                  eps_d, phi.numpy(), ksi.numpy())
+
+    def sweep(self, terms, u, v, w, d_in, phi, ksi, h, alpha, d_out, lo, hi):
+        dl, hh, ww = u.t.shape
+        self.o.lib.o_sweep_slab(terms[0].numpy(), terms[1].numpy(), u.t.numpy(), v.t.numpy(), w.t.numpy(),
+                                *[t.numpy() for t in d_in], phi.numpy(), ksi.numpy(), ww, hh, u.A, u.dg, lo - u.A,
+                                hi - u.A, h[0], h[1], h[2], alpha, *[t.numpy() for t in d_out])
+
+    def add3(self, flow, d):
+        for c in range(3):
+            flow[c].t.add_(d[c])  # one rounded fp32 add per element == add_3d.cu:37-40
+
+    def median(self, src, dst_t, radius, lo, hi):
+        dl, hh, ww = src.t.shape
+        rc = self.o.lib.o_median_slab(src.t.numpy(), dst_t.numpy(), ww, hh, src.A, src.dg, lo - src.A, hi - src.A, radius)
+        if rc != 0:
+            raise ValueError("unsupported median radius")
+
+    def absmax(self, s):
+        return float(s.t.abs().max())
+
+    def from_numpy_full(self, a):
+        return torch.from_numpy(np.ascontiguousarray(a, np.float32).copy())
+
+    def to_numpy(self, t, w):
+        return t[:, :, :w].contiguous().numpy()
+
+
+# =====================================================================================================
+class ShardedFlowSolver:
+    """Coarse-to-fine solve of OpticalFlowE::ComputeFlow (optical_flow_e.cpp:132-601) with every large
+    level sharded along z over the ranks of `group`."""
+
+    def __init__(self, backend, rank=None, world=None, min_planes_per_rank=16, min_voxels_per_rank=1 << 21):
+        self.be = backend
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        self.min_planes = min_planes_per_rank
+        self.min_voxels = min_voxels_per_rank
+        self.stats = {"sharded_levels": 0, "replicated_levels": 0, "exchanges": 0, "exchange_bytes": 0}
+
+    # ---- neighbour exchange of ghost planes -------------------------------------------------------
+    def _exchange(self, fields, A, B, a, b, H, D):
+        """fill ghosts [A,a) and [b,B) of every tensor in `fields` from the z neighbours' owned planes"""
+        if self.world == 1:
+            return
+        ops = []
+        lo_n, hi_n = self.rank - 1, self.rank + 1
+        for t in fields:
+            if lo_n >= 0 and a > A:  # my lower ghosts <- rank-1's top planes; rank-1's upper ghosts <- my bottom planes
+                ops.append(dist.P2POp(dist.irecv, t[0:a - A], lo_n))
+                ops.append(dist.P2POp(dist.isend, t[a - A:a - A + min(H, b - a)], lo_n))
+            if hi_n < self.world and B > b:
+                ops.append(dist.P2POp(dist.isend, t[b - A - min(H, b - a):b - A], hi_n))
+                ops.append(dist.P2POp(dist.irecv, t[b - A:B - A], hi_n))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+            self.stats["exchanges"] += 1
+            self.stats["exchange_bytes"] += sum(op.tensor.numel() * 4 for op in ops if op.op is dist.isend)
+
+    def _is_sharded(self, dims, H):
+        w, h, d = dims
+        if self.world == 1:
+            return False
+        per = d // self.world
+        return per >= max(self.min_planes, 2 * H) and w * h * per >= self.min_voxels
+
+    # ---- the solve ---------------------------------------------------------------------------------
+    def compute(self, frame_0, frame_1, params=None, level_cb=None):
+        """frame_0/frame_1: FULL volumes (numpy (D,H,W)) given to every rank.  Returns (a, b, [u,v,w]):
+        this rank's owned plane range of the finest level and numpy arrays of those planes (the full
+        volume on every rank if the finest level was too small to shard)."""
+        from .api import level_schedule
+        be = self.be
+        P = dict(DEFAULTS)
+        P.update(params or {})
+        D, Hh, W = frame_0.shape
+        inner, outer = int(P["inner_iterations_count"]), int(P["outer_iterations_count"])
+        H = inner + 1
+        sched = self._schedule(W, Hh, D, P)
+        F0 = be.from_numpy_full(frame_0)
+        F1 = be.from_numpy_full(frame_1)
+        if P["gaussian_sigma"] > 0:
+            F0, F1 = be.blur(F0, P["gaussian_sigma"]), be.blur(F1, P["gaussian_sigma"])
+        fullF0 = Slab(F0, 0, D, W)
+        fullF1 = Slab(F1, 0, D, W)
+        prev = None  # (dims, [u,v,w] Slabs, valid_lo, valid_hi)
+        for (level, dims, h) in sched:
+            w, hh, d = dims
+            sharded = self._is_sharded(dims, H)
+            a, b = own_range(d, self.rank, self.world) if sharded else (0, d)
+            A, B = (max(0, a - H), min(d, b + H)) if sharded else (0, d)
+            dl = B - A
+            self.stats["sharded_levels" if sharded else "replicated_levels"] += 1
+
+            # ---- flow at this level: zeros, or box-prolongation of the previous level (:304-344) -----
+            flow = [Slab(be.zeros(w, hh, dl), A, d, w) for _ in range(3)]
+            if prev is not None:
+                pdims, pflow, pv_lo, pv_hi = prev
+                s_lo, s_hi = source_range(a, b, pdims[2], d)
+                assert pv_lo <= s_lo and s_hi <= pv_hi, "prolongation needs planes outside the valid range"
+                for c in range(3):
+                    src = Slab(pflow[c].planes(s_lo, s_hi), s_lo, pdims[2], pdims[0])
+                    be.resample(src, pdims, dims, A, a, b, out=flow[c])
+                self._exchange([f.t for f in flow], A, B, a, b, H, d)
+            # ---- frames of this level, resampled from the replicated full-resolution frames -------------
+            hz = h[2]
+            reach = int(math.ceil(be.absmax(flow[2]) / float(hz))) + 2 if prev is not None else 1
+            A1, B1 = max(0, A - reach), min(d, B + reach)
+            if level == 0:
+                f0l = Slab(fullF0.planes(A, B), A, d, w)
+                f1l = Slab(fullF1.planes(A1, B1), A1, d, w)
+            else:
+                f0l = self._frame(fullF0, (W, Hh, D), dims, A, B)
+                f1l = self._frame(fullF1, (W, Hh, D), dims, A1, B1)
+            # ---- warp + derivatives on every plane the solver touches ----------------------------------
+            lo1 = A if A == 0 else A + 1
+            hi1 = B if B == d else B - 1
+            terms = be.warp_terms(f0l, f1l, flow[0], flow[1], flow[2], h, lo1, hi1)
+            # ---- solver (cuda_operation_solve.cpp:183-257) ----------------------------------------------
+            d_cur = [be.zeros(w, hh, dl) for _ in range(3)]
+            d_alt = [be.zeros(w, hh, dl) for _ in range(3)]
+            phi, ksi = be.zeros(w, hh, dl), be.zeros(w, hh, dl)
+            for _ in range(outer):
+                be.phi_ksi(terms, flow[0], flow[1], flow[2], d_cur[0], d_cur[1], d_cur[2], h, P["equation_smoothness"],
+                           P["equation_data"], phi, ksi, lo1, hi1)
+                for j in range(1, inner + 1):
+                    lo = A if A == 0 else A + 1 + j
+                    hi = B if B == d else B - 1 - j
+                    be.sweep(terms, flow[0], flow[1], flow[2], d_cur, phi, ksi, h, P["equation_alpha"], d_alt, lo, hi)
+                    d_cur, d_alt = d_alt, d_cur
+                if sharded:
+                    self._exchange(d_cur, A, B, a, b, H, d)
+            # ---- u += du (:420-438), valid on the whole buffer because the last exchange refreshed du ----
+            be.add3(flow, d_cur)
+            # ---- median (:443-473) on everything whose +-r/2 neighbourhood is valid ---------------------
+            r = int(P["median_radius"])
+            r2 = (r - 1 if (r % 2 == 0 and r > 1) else r) // 2
+            m_lo = A if A == 0 else A + r2
+            m_hi = B if B == d else B - r2
+            for c in range(3):
+                be.median(flow[c], d_alt[c], r, m_lo, m_hi)
+                flow[c] = Slab(d_alt[c], A, d, w)
+                d_alt[c] = None
+            prev = (dims, flow, m_lo, m_hi)
+            if level_cb is not None:
+                level_cb(level, dims, (a, b), [be.to_numpy(f.planes(a, b), w) for f in flow])
+        dims, flow, _, _ = prev
+        a, b = own_range(dims[2], self.rank, self.world) if self._is_sharded(dims, H) else (0, dims[2])
+        return a, b, [be.to_numpy(f.planes(a, b), dims[0]) for f in flow]
+
+    def _frame(self, full, full_whd, dims, lo, hi):
+        """planes [lo, hi) of a level frame, box-resampled from the replicated full-resolution frame
+        (optical_flow_e.cpp:279-299: always from full resolution)"""
+        be = self.be
+        w, hh, d = dims
+        s_lo, s_hi = source_range(lo, hi, full_whd[2], d)
+        src = Slab(full.planes(s_lo, s_hi), s_lo, full_whd[2], full_whd[0])
+        out = Slab(be.empty(w, hh, hi - lo), lo, d, w)
+        return be.resample(src, full_whd, dims, lo, lo, hi, out=out)
+
+    @staticmethod
+    def _schedule(W, H, D, P):
+        from .api import level_schedule
+        return level_schedule(W, H, D, P["warp_scale_factor"], P["warp_levels_count"])

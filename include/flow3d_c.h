@@ -51,6 +51,21 @@ typedef struct flow3d_params {
 
 typedef struct flow3d_solver flow3d_solver; /* opaque */
 
+/* z-slab view of a level that is sharded along z across GPUs (one process per GPU).  The buffers
+ * passed with a slab hold `dims[2]` consecutive planes of the level, local plane 0 being global plane
+ * `z0_global`; mirror boundary conditions and the face weights apply at the GLOBAL faces
+ * (0 and depth_global-1) only, elsewhere the z neighbours are ordinary (ghost) planes of the buffer.
+ * [z_begin, z_end) is the range of local planes the call computes; every plane it reads (z_begin-1 ..
+ * z_end for the 7-point stencils, +-2 for the 5^3 median) must exist in the buffer unless it lies
+ * beyond a global face.  The reference's own precedent is the z-slab + 1-plane mirrored halo scheme of
+ * its out-of-core path (src/cuda_operations/partial_data/cuda_operation_solve_p.cpp:358-417). */
+typedef struct flow3d_zslab {
+  size_t z0_global;
+  size_t depth_global;
+  size_t z_begin;
+  size_t z_end;
+} flow3d_zslab;
+
 /* ---- misc ------------------------------------------------------------------------------- */
 int flow3d_version(void);
 const char* flow3d_status_string(int status);
@@ -162,6 +177,37 @@ int flow3d_add3(float* u, float* v, float* w, const float* du, const float* dv, 
  * and median_3d (src/kernels/median_3d.cu:49-299).  in != out. */
 int flow3d_median(const float* in, float* out, const size_t dims[3], size_t ld, size_t radius,
                   void* stream);
+
+/* ---- z-slab (multi-GPU) variants: identical arithmetic, boundary handling per flow3d_zslab ------ */
+int flow3d_sweep_slab(const float* fx, const float* fy, const float* fz, const float* ft,
+                      const float* u, const float* v, const float* w, const float* du,
+                      const float* dv, const float* dw, const float* phi, const float* ksi,
+                      const size_t dims[3], size_t ld, const flow3d_zslab* slab, const float h[3],
+                      float alpha, float* du_out, float* dv_out, float* dw_out, void* stream);
+int flow3d_phi_ksi_slab(const float* fx, const float* fy, const float* fz, const float* ft,
+                        const float* u, const float* v, const float* w, const float* du,
+                        const float* dv, const float* dw, const size_t dims[3], size_t ld,
+                        const flow3d_zslab* slab, const float h[3], float eps_smooth, float eps_data,
+                        float* phi, float* ksi, void* stream);
+/* f1 lives in its own slab (f1_dims[2] planes starting at global plane f1_z0_global) because the warp
+ * reaches max|w|/hz planes beyond the planes being computed */
+int flow3d_warp_derivatives_slab(const float* f0, const float* f1, size_t f1_z0_global,
+                                 size_t f1_depth_local, const float* u, const float* v,
+                                 const float* w, const size_t dims[3], size_t ld,
+                                 const flow3d_zslab* slab, const float h[3], float* fx, float* fy,
+                                 float* fz, float* ft, void* stream);
+int flow3d_median_slab(const float* in, float* out, const size_t dims[3], size_t ld,
+                       const flow3d_zslab* slab, size_t radius, void* stream);
+/* resample with the input and the output each given as a slab of its level; x and y passes run on
+ * all local input planes, the z pass produces output planes [out_slab->z_begin, z_end).
+ * tmp_a: >= ld(out_w)*in_h*in_depth_local, tmp_b: >= ld(out_w)*out_h*in_depth_local floats */
+int flow3d_resample_slab(const float* in, const size_t in_dims[3], size_t in_ld,
+                         const flow3d_zslab* in_slab, float* out, const size_t out_dims[3],
+                         size_t out_ld, const flow3d_zslab* out_slab, float* tmp_a, float* tmp_b,
+                         void* stream);
+/* max |x| over the w*h*d samples of a pitched device volume (padding columns ignored), written to
+ * *out_dev (one device float) */
+int flow3d_absmax(const float* dev, const size_t dims[3], size_t ld, float* out_dev, void* stream);
 
 /* ---- solver object -------------------------------------------------------------------------
  * Replaces OpticalFlowE::{Initialize, ComputeFlow, Destroy}

@@ -45,6 +45,13 @@ inline long mirror(long i, long n) {
   return i;
 }
 
+// z-slab view (multi-GPU sharding): local plane zl of a buffer whose plane 0 is global plane z0g of
+// a level of global depth dg; reflect-101 applies at the global faces only.
+struct Slab {
+  long z0g, dg, zs, ze;
+};
+inline long zn(const Slab& s, long zl, long dz) { return mirror(s.z0g + zl + dz, s.dg) - s.z0g; }
+
 }  // namespace
 
 extern "C" {
@@ -205,14 +212,18 @@ void o_resample(const float* in, const size_t* in_dims, float* out, const size_t
   o_resample_axis(tmp_b, d0, out, out_dims[2], 2);
 }
 
-// registration_3d.cu:46-80
-void o_warp(const float* f0, const float* f1, const float* u, const float* v, const float* wv,
-            size_t width, size_t height, size_t depth, float hx, float hy, float hz, float* out) {
+// registration_3d.cu:46-80.  Slab form: f0,u,v,w,out are slabs (local plane 0 = global z0g) of a level of
+// global depth `depth`; f1 is its own slab starting at global plane f1_z0g.  Computes local planes
+// [zs, ze).  The plain form is the slab form with z0g = 0 and the whole range.
+void o_warp_slab(const float* f0, const float* f1, long f1_z0g, const float* u, const float* v,
+                 const float* wv, size_t width, size_t height, size_t depth, long z0g, long zs, long ze,
+                 float hx, float hy, float hz, float* out) {
 #pragma omp parallel for schedule(static)
-  for (long gz = 0; gz < (long)depth; ++gz)
+  for (long lz = zs; lz < ze; ++lz)
     for (size_t gy = 0; gy < height; ++gy)
       for (size_t gx = 0; gx < width; ++gx) {
-        size_t c = IDX(gx, gy, gz, width, height);
+        const long gz = z0g + lz;
+        size_t c = IDX(gx, gy, lz, width, height);
         // registration_3d.ptx: rcp.rn(h) then ONE fma.rn per coordinate
         float x_f = std::fmaf(1.f / hx, u[c], (float)(unsigned)gx);
         float y_f = std::fmaf(1.f / hy, v[c], (float)(unsigned)gy);
@@ -236,33 +247,41 @@ void o_warp(const float* f0, const float* f1, const float* u, const float* v, co
           float w10 = (delta_x) * (1.f - delta_y);
           float w01 = (1.f - delta_x) * (delta_y);
           float w11 = (delta_x) * (delta_y);
-          float value_0 = w10 * f1[IDX(x_1, y, z, width, height)];
-          value_0 = std::fmaf(w00, f1[IDX(x, y, z, width, height)], value_0);
-          value_0 = std::fmaf(w01, f1[IDX(x, y_1, z, width, height)], value_0);
-          value_0 = std::fmaf(w11, f1[IDX(x_1, y_1, z, width, height)], value_0);
-          float value_1 = w10 * f1[IDX(x_1, y, z_1, width, height)];
-          value_1 = std::fmaf(w00, f1[IDX(x, y, z_1, width, height)], value_1);
-          value_1 = std::fmaf(w01, f1[IDX(x, y_1, z_1, width, height)], value_1);
-          value_1 = std::fmaf(w11, f1[IDX(x_1, y_1, z_1, width, height)], value_1);
+          const long zl0 = z - f1_z0g, zl1 = z_1 - f1_z0g;  // planes of the frame-1 slab
+          float value_0 = w10 * f1[IDX(x_1, y, zl0, width, height)];
+          value_0 = std::fmaf(w00, f1[IDX(x, y, zl0, width, height)], value_0);
+          value_0 = std::fmaf(w01, f1[IDX(x, y_1, zl0, width, height)], value_0);
+          value_0 = std::fmaf(w11, f1[IDX(x_1, y_1, zl0, width, height)], value_0);
+          float value_1 = w10 * f1[IDX(x_1, y, zl1, width, height)];
+          value_1 = std::fmaf(w00, f1[IDX(x, y, zl1, width, height)], value_1);
+          value_1 = std::fmaf(w01, f1[IDX(x, y_1, zl1, width, height)], value_1);
+          value_1 = std::fmaf(w11, f1[IDX(x_1, y_1, zl1, width, height)], value_1);
           out[c] = std::fmaf(1.f - delta_z, value_0, delta_z * value_1);
         }
       }
 }
 
-// compute_phi_ksi_3d, solve_3d.cu:177-260 (neighbour mirroring :73-75,87-170)
-void o_phi_ksi(const float* f0, const float* f1, const float* u, const float* v, const float* wv,
-               const float* du, const float* dv, const float* dw, size_t width, size_t height,
-               size_t depth, float hx, float hy, float hz, float eq_smooth, float eq_data,
-               float* phi, float* ksi) {
-  const long W = width, H = height, D = depth;
+void o_warp(const float* f0, const float* f1, const float* u, const float* v, const float* wv,
+            size_t width, size_t height, size_t depth, float hx, float hy, float hz, float* out) {
+  o_warp_slab(f0, f1, 0, u, v, wv, width, height, depth, 0, 0, (long)depth, hx, hy, hz, out);
+}
+
+// compute_phi_ksi_3d, solve_3d.cu:177-260 (neighbour mirroring :73-75,87-170).  Slab form: buffers are
+// z-slabs (plane 0 = global z0g) of a level of global depth dg; local planes [zs, ze) are computed.
+void o_phi_ksi_slab(const float* f0, const float* f1, const float* u, const float* v, const float* wv,
+                    const float* du, const float* dv, const float* dw, size_t width, size_t height,
+                    long z0g, long dg, long zs, long ze, float hx, float hy, float hz, float eq_smooth,
+                    float eq_data, float* phi, float* ksi) {
+  const long W = width, H = height;
+  const Slab sl{z0g, dg, zs, ze};
 #pragma omp parallel for schedule(static)
-  for (long z = 0; z < D; ++z)
+  for (long z = zs; z < ze; ++z)
     for (long y = 0; y < H; ++y)
       for (long x = 0; x < W; ++x) {
         size_t c = IDX(x, y, z, W, H);
         size_t xp = IDX(mirror(x + 1, W), y, z, W, H), xm = IDX(mirror(x - 1, W), y, z, W, H);
         size_t yp = IDX(x, mirror(y + 1, H), z, W, H), ym = IDX(x, mirror(y - 1, H), z, W, H);
-        size_t zp = IDX(x, y, mirror(z + 1, D), W, H), zm = IDX(x, y, mirror(z - 1, D), W, H);
+        size_t zp = IDX(x, y, zn(sl, z, 1), W, H), zm = IDX(x, y, zn(sl, z, -1), W, H);
 
         float dux = (u[xp] - u[xm] + du[xp] - du[xm]) / (2.f * hx);
         float duy = (u[yp] - u[ym] + du[yp] - du[ym]) / (2.f * hy);
@@ -311,20 +330,30 @@ void o_phi_ksi(const float* f0, const float* f1, const float* u, const float* v,
       }
 }
 
-// solve_3d, solve_3d.cu:423-507: one Jacobi sweep (du,dv,dw) -> (tdu,tdv,tdw)
-void o_sweep(const float* f0, const float* f1, const float* u, const float* v, const float* wv,
-             const float* du, const float* dv, const float* dw, const float* phi, const float* ksi,
-             size_t width, size_t height, size_t depth, float hx, float hy, float hz, float alpha,
-             float* tdu, float* tdv, float* tdw) {
-  const long W = width, H = height, D = depth;
+void o_phi_ksi(const float* f0, const float* f1, const float* u, const float* v, const float* wv,
+               const float* du, const float* dv, const float* dw, size_t width, size_t height,
+               size_t depth, float hx, float hy, float hz, float eq_smooth, float eq_data,
+               float* phi, float* ksi) {
+  o_phi_ksi_slab(f0, f1, u, v, wv, du, dv, dw, width, height, 0, (long)depth, 0, (long)depth, hx, hy, hz,
+                 eq_smooth, eq_data, phi, ksi);
+}
+
+// solve_3d, solve_3d.cu:423-507: one Jacobi sweep (du,dv,dw) -> (tdu,tdv,tdw); slab form as above
+void o_sweep_slab(const float* f0, const float* f1, const float* u, const float* v, const float* wv,
+                  const float* du, const float* dv, const float* dw, const float* phi,
+                  const float* ksi, size_t width, size_t height, long z0g, long dg, long zs, long ze,
+                  float hx, float hy, float hz, float alpha, float* tdu, float* tdv, float* tdw) {
+  const long W = width, H = height;
+  const Slab sl{z0g, dg, zs, ze};
 #pragma omp parallel for schedule(static)
-  for (long z = 0; z < D; ++z)
+  for (long z = zs; z < ze; ++z)
     for (long y = 0; y < H; ++y)
       for (long x = 0; x < W; ++x) {
+        const long zglob = z0g + z;
         size_t c = IDX(x, y, z, W, H);
         size_t ixp = IDX(mirror(x + 1, W), y, z, W, H), ixm = IDX(mirror(x - 1, W), y, z, W, H);
         size_t iyp = IDX(x, mirror(y + 1, H), z, W, H), iym = IDX(x, mirror(y - 1, H), z, W, H);
-        size_t izp = IDX(x, y, mirror(z + 1, D), W, H), izm = IDX(x, y, mirror(z - 1, D), W, H);
+        size_t izp = IDX(x, y, zn(sl, z, 1), W, H), izm = IDX(x, y, zn(sl, z, -1), W, H);
 
         float fx = (f0[ixp] - f0[ixm] + f1[ixp] - f1[ixm]) / (4.f * hx);
         float fy = (f0[iyp] - f0[iym] + f1[iyp] - f1[iym]) / (4.f * hy);
@@ -343,8 +372,8 @@ void o_sweep(const float* f0, const float* f1, const float* u, const float* v, c
         float xm = (x > 0) * hx_2;
         float yp = (y < H - 1) * hy_2;
         float ym = (y > 0) * hy_2;
-        float zp = (z < D - 1) * hz_2;
-        float zm = (z > 0) * hz_2;
+        float zp = (zglob < dg - 1) * hz_2;
+        float zm = (zglob > 0) * hz_2;
 
         float phi_xp = (phi[ixp] + phi[c]) / 2.f;
         float phi_xm = (phi[ixm] + phi[c]) / 2.f;
@@ -398,6 +427,14 @@ void o_sweep(const float* f0, const float* f1, const float* u, const float* v, c
       }
 }
 
+void o_sweep(const float* f0, const float* f1, const float* u, const float* v, const float* wv,
+             const float* du, const float* dv, const float* dw, const float* phi, const float* ksi,
+             size_t width, size_t height, size_t depth, float hx, float hy, float hz, float alpha,
+             float* tdu, float* tdv, float* tdw) {
+  o_sweep_slab(f0, f1, u, v, wv, du, dv, dw, phi, ksi, width, height, 0, (long)depth, 0, (long)depth, hx, hy,
+               hz, alpha, tdu, tdv, tdw);
+}
+
 // CudaOperationSolve::Execute, cuda_operation_solve.cpp:183-257.  On return du/dv/dw hold the
 // final iterate (the reference swaps pointers; here we copy when the sweep count is odd).
 // scratch: 5 volumes (phi, ksi, tdu, tdv, tdw).
@@ -441,20 +478,21 @@ void o_add(float* a, const float* b, size_t n) {
 // length; 1 -> copy; even -> radius-1; supported 3,5,7).  Selection == element [len/2] of the sorted
 // window.  Returns 0 on success, -1 for an unsupported radius (the reference prints and leaves the
 // output untouched).
-int o_median(const float* in, float* out, size_t width, size_t height, size_t depth,
-             size_t radius) {
-  const size_t n = width * height * depth;
+int o_median_slab(const float* in, float* out, size_t width, size_t height, long z0g, long dg, long zs,
+                  long ze, size_t radius) {
+  const Slab sl{z0g, dg, zs, ze};
+  const size_t plane = width * height;
   if (radius == 1) {
-    std::memcpy(out, in, n * sizeof(float));
+    std::memcpy(out + zs * plane, in + zs * plane, (size_t)(ze - zs) * plane * sizeof(float));
     return 0;
   }
   if (radius % 2 == 0) radius -= 1;
   if (radius < 3 || radius > 7) return -1;
   const long r2 = (long)radius / 2;
-  const long W = width, H = height, D = depth;
+  const long W = width, H = height;
   const size_t len = radius * radius * radius;
 #pragma omp parallel for schedule(static)
-  for (long z = 0; z < D; ++z) {
+  for (long z = zs; z < ze; ++z) {
     std::vector<float> buf(len);
     for (long y = 0; y < H; ++y)
       for (long x = 0; x < W; ++x) {
@@ -462,12 +500,37 @@ int o_median(const float* in, float* out, size_t width, size_t height, size_t de
         for (long iz = -r2; iz <= r2; ++iz)
           for (long iy = -r2; iy <= r2; ++iy)
             for (long ix = -r2; ix <= r2; ++ix)
-              buf[k++] = in[IDX(mirror(x + ix, W), mirror(y + iy, H), mirror(z + iz, D), W, H)];
+              buf[k++] = in[IDX(mirror(x + ix, W), mirror(y + iy, H), zn(sl, z, iz), W, H)];
         std::nth_element(buf.begin(), buf.begin() + len / 2, buf.end());
         out[IDX(x, y, z, W, H)] = buf[len / 2];
       }
   }
   return 0;
+}
+
+int o_median(const float* in, float* out, size_t width, size_t height, size_t depth,
+             size_t radius) {
+  return o_median_slab(in, out, width, height, 0, (long)depth, 0, (long)depth, radius);
+}
+
+// z pass of the resample between slabs: input slab (plane 0 = global in_z0g, global depth in_dg) ->
+// output slab (out_z0g, out_dg), output local planes [zs, ze); same tap arithmetic in global indices.
+void o_resample_z_slab(const float* in, size_t w, size_t h, long in_z0g, long in_dg, float* out,
+                       long out_z0g, long out_dg, long zs, long ze) {
+#pragma omp parallel for schedule(static)
+  for (long z = zs; z < ze; ++z) {
+    std::vector<float> frac((size_t)in_dg + 4);
+    int li, cnt;
+    float norm = resample_taps((size_t)in_dg, (size_t)out_dg, (unsigned)(out_z0g + z), &li, &cnt, frac.data(),
+                               (int)in_dg + 4);
+    for (size_t y = 0; y < h; ++y)
+      for (size_t x = 0; x < w; ++x) {
+        float value = 0.f;
+        for (int j = 0; j < cnt; j++)
+          value = std::fmaf(frac[j], in[IDX(x, y, (size_t)(li + j - in_z0g), w, h)], value);
+        out[IDX(x, y, z, w, h)] = value * norm;
+      }
+  }
 }
 
 struct OracleParams {
