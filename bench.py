@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--size", type=int, default=0, help="cube edge (default 512)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--replicas", action="store_true", help="N>1: independent 512^3 replicas instead of one sharded solve")
     return ap.parse_args()
 
 
@@ -183,7 +184,122 @@ def run_reference(args, rank, world):
 
 
 # ---------------------------------------------------------------------------------------------------
+def run_sharded(args, rank, world, local_rank):
+    """N > 1: ONE volume pair (BASELINE configs[3]: synthetic 1024^3) z-sharded over the N GPUs,
+    neighbour halo exchange over NVLink (NCCL send/recv), cuda_flow3d_b200/dist.py."""
+    import torch
+    import torch.distributed as dist
+    import cuda_flow3d_b200 as pkg
+    from cuda_flow3d_b200.dist import CabiBackend, ShardedFlowSolver
+    L = pkg.load()
+    pkg.require_device()
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    be = CabiBackend(local_rank)
+    n = args.size or 1024
+    W = H = D = n
+    P = dict(pkg.DEFAULTS)
+    ld = be.ld(W)
+    dev = be.dev
+    st = torch.cuda.current_stream()
+    sp = C.c_void_p(st.cuda_stream)
+    f0 = torch.empty((D, H, ld), dtype=torch.float32, device=dev)
+    f1 = torch.empty((D, H, ld), dtype=torch.float32, device=dev)
+    pkg._lib.check(L.flow3d_synth_pair(W, H, D, 0, D, ld, SEED, C.c_void_p(f0.data_ptr()), C.c_void_p(f1.data_ptr()),
+                                       None, None, None, sp), "synth")
+    solver = ShardedFlowSolver(be)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return solver.compute(f0, f1, P, width=W, return_device=True)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    solver.profile = True
+    solver.sweep_events = []
+    for k in solver.stats:
+        solver.stats[k] = 0
+    L.flow3d_reset_launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(args.steps):
+        a, b, flow = step()
+    e1.record(st)
+    barrier()
+    clocks = sampler.stop()
+    launches = int(L.flow3d_launch_count())
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = (W * H * D) / (ms_per_step / 1000.0) / 1e6
+    sw_ms, sw_units = solver.sweep_profile()
+    solver.profile = False
+    stats = dict(solver.stats)
+
+    # e2e: every rank uploads both (replicated) frames from pinned host memory and downloads its shard
+    e2e = None
+    if not args.no_e2e:
+        h0 = torch.empty((D, H, ld), dtype=torch.float32, pin_memory=True)
+        h1 = torch.empty((D, H, ld), dtype=torch.float32, pin_memory=True)
+        h0.copy_(f0)
+        h1.copy_(f1)
+        ho = [torch.empty((b - a, H, ld), dtype=torch.float32, pin_memory=True) for _ in range(3)]
+        step()  # untimed: lets the allocator settle after the pinned allocations
+        barrier()
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x0.record(st)
+        f0.copy_(h0, non_blocking=True)
+        f1.copy_(h1, non_blocking=True)
+        a, b, flow = step()
+        for c in range(3):
+            ho[c].copy_(flow[c], non_blocking=True)
+        x1.record(st)
+        barrier()
+        t = torch.tensor([x0.elapsed_time(x1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_ms = float(t.item())
+        e2e = {"value": (W * H * D) / (e_ms / 1000.0) / 1e6, "unit": "Mvoxel/s",
+               "h2d_bytes_per_step": 2 * D * H * ld * 4, "d2h_bytes_per_step": 3 * (b - a) * H * ld * 4,
+               "ms_per_step": e_ms, "steps": 1, "host_memory": "pinned",
+               "note": "per rank: both full frames up (replicated), own z-shard of the flow down"}
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        achieved = SWEEP_BYTES * sw_units / (sw_ms / 1000.0) / 1e9 if sw_ms > 0 else 0.0
+        nsum, nlev = level_voxel_sum(pkg, W, H, D, P)
+        line = {
+            "metric": "Mvoxel/s per full pyramid flow solve", "value": value, "unit": "Mvoxel/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "synthetic %d^3 pair (BASELINE configs[3]) z-sharded over %d GPUs, default "
+                                   "parameters (%d levels x 40 outer x 5 inner sweeps, median 5, sigma 2)" % (n, world, nlev),
+                       "parallelism": "z-slabs, %d ghost planes, one NCCL send/recv neighbour exchange per outer "
+                                      "iteration; coarse levels replicated" % (P["inner_iterations_count"] + 1),
+                       "inputs_larger_than_l2": True, "level_voxels": nsum,
+                       "sharded_levels_per_step": stats["sharded_levels"] / max(1, args.steps),
+                       "replicated_levels_per_step": stats["replicated_levels"] / max(1, args.steps),
+                       "halo_bytes_sent_per_step_rank0": stats["exchange_bytes"] / max(1, args.steps),
+                       "parity": "bit-identical to the single-GPU solve (tests/test_dist_gpu.py)"},
+            "clocks": clocks, "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "sweep_kernel (rank 0, its z-slab incl. ghost planes)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_voxel_sweep": SWEEP_BYTES,
+                         "voxel_sweeps": sw_units, "traffic": None},
+        }
+        if e2e:
+            line["e2e"] = e2e
+        print(json.dumps(line))
+    dist.destroy_process_group()
+
+
 def run_ours(args, rank, world, local_rank):
+    if world > 1 and not args.replicas:
+        return run_sharded(args, rank, world, local_rank)
     import torch
     import cuda_flow3d_b200 as pkg
     L = pkg.load()

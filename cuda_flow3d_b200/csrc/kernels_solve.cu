@@ -86,20 +86,48 @@ struct SweepArgs {
   int zchunk;
   int pf;  // prefetch distance in planes (0 = off)
   int zs, ze;  // compute range (local planes)
+  int lpr;     // lanes per row segment (32, 16 or 8)
 };
+
+// Lane layout: a warp covers 32/lpr consecutive rows x (lpr*VEC) columns (lpr = lanes per row, a power
+// of two chosen per level so that ceil(w / (lpr*VEC)) tiles waste as few lanes as possible -- level
+// widths like 397 would otherwise leave a quarter of the lanes idle).
+struct LaneMap {
+  int sub;         // lane index within its row segment
+  int x0, y;       // first column of this lane's VEC group (clamped for idle lanes), row
+  bool active;     // false: idle lane (x beyond the volume), shadows the last group, stores nothing
+  bool row_ok;     // false: row beyond the volume (idle, clamped to the last row)
+  bool left_edge, right_edge;
+};
+template <int VEC>
+__device__ __forceinline__ LaneMap lane_map(int lpr, int w, int h) {
+  LaneMap m;
+  const int lane = threadIdx.x;
+  m.sub = lane & (lpr - 1);
+  const int rows_per_warp = 32 / lpr;
+  const int y_raw = (blockIdx.y * blockDim.y + threadIdx.y) * rows_per_warp + lane / lpr;
+  m.row_ok = y_raw < h;
+  m.y = m.row_ok ? y_raw : h - 1;
+  const int x0_raw = (blockIdx.x * lpr + m.sub) * VEC;
+  m.active = (x0_raw < w) && m.row_ok;
+  m.x0 = (x0_raw < w) ? x0_raw : ((w - 1) / VEC) * VEC;
+  m.left_edge = m.sub == 0;
+  m.right_edge = m.sub == lpr - 1;
+  return m;
+}
 
 // x-neighbour values of a VEC-wide register group: left[i] / right[i] are the values at x-1 / x+1
 // of element i, taken from the group itself, the adjacent lanes (shuffle) or, at the ends of the
-// warp's row segment, from `halo` (lane 0: value at x0-1, lane 31: value at x0+VEC).  At the volume
+// lane's row segment, from `halo` (first lane: value at x0-1, last lane: value at x0+VEC).  At the volume
 // faces the reflect-101 neighbour is substituted (x=0 -> value at 1, x=w-1 -> value at w-2), which
 // is what the reference's shared-memory halo holds (solve_3d.cu:326-355).
 template <int VEC>
-__device__ __forceinline__ void x_neighbours(const Vec<VEC>& c, float halo, int lane, int x0, int w,
-                                             Vec<VEC>& left, Vec<VEC>& right) {
+__device__ __forceinline__ void x_neighbours(const Vec<VEC>& c, float halo, bool left_edge, bool right_edge,
+                                             int x0, int w, Vec<VEC>& left, Vec<VEC>& right) {
   float from_left = __shfl_up_sync(0xffffffffu, c.v[VEC - 1], 1);
   float from_right = __shfl_down_sync(0xffffffffu, c.v[0], 1);
-  if (lane == 0) from_left = halo;
-  if (lane == 31) from_right = halo;
+  if (left_edge) from_left = halo;
+  if (right_edge) from_right = halo;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     float l = (i > 0) ? c.v[i - 1] : from_left;
@@ -117,21 +145,20 @@ __device__ __forceinline__ void x_neighbours(const Vec<VEC>& c, float halo, int 
 template <int VEC, int UNROLL>
 __global__ void __launch_bounds__(128) sweep_kernel(const SweepArgs a) {
   const Dims g = a.g;
-  const int lane = threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (y >= g.h) return;  // whole warp leaves together
-  const int x0_raw = (blockIdx.x * 32 + lane) * VEC;
-  const bool active = x0_raw < g.w;
-  const int x0 = active ? x0_raw : ((g.w - 1) / VEC) * VEC;  // idle lanes shadow the last group
+  const LaneMap lm = lane_map<VEC>(a.lpr, g.w, g.h);
+  if ((int)((blockIdx.y * blockDim.y + threadIdx.y) * (32 / a.lpr)) >= g.h) return;  // whole warp leaves together
+  const int y = lm.y;
+  const bool active = lm.active;
+  const int x0 = lm.x0;  // idle lanes shadow the last group / last row
   const int z_begin = a.zs + blockIdx.z * a.zchunk;
   const int z_end = min(a.ze, z_begin + a.zchunk);
   if (z_begin >= z_end) return;
 
   const int ym = mirror_idx(y - 1, g.h);
   const int yp = mirror_idx(y + 1, g.h);
-  // halo column of this lane: lane 0 -> x0-1, lane 31 -> x0+VEC (mirrored at the faces); the other
-  // lanes re-read their own first element (an L1 hit) so that the load needs no branch
-  const int xh = (lane == 0) ? mirror_idx(x0 - 1, g.w) : ((lane == 31) ? mirror_idx(x0 + VEC, g.w) : x0);
+  // halo column of this lane: first lane of a row segment -> x0-1, last -> x0+VEC (mirrored at the
+  // faces); the other lanes re-read their own first element (an L1 hit) so the load needs no branch
+  const int xh = lm.left_edge ? mirror_idx(x0 - 1, g.w) : (lm.right_edge ? mirror_idx(x0 + VEC, g.w) : x0);
 
   // 32-bit element offsets (volumes hold < 2^32 elements; checked by the launcher): one
   // IMAD.WIDE per load instead of a 64-bit add pair
@@ -230,10 +257,10 @@ __global__ void __launch_bounds__(128) sweep_kernel(const SweepArgs a) {
     const float hSw = __fadd_rn(__ldg(a.w + oh), __ldg(a.dw + oh));
     const float hph = __ldg(a.phi + oh);
     Vec<VEC> Su_xm, Su_xp, Sv_xm, Sv_xp, Sw_xm, Sw_xp, ph_xm, ph_xp;
-    x_neighbours<VEC>(Su_c, hSu, lane, x0, g.w, Su_xm, Su_xp);
-    x_neighbours<VEC>(Sv_c, hSv, lane, x0, g.w, Sv_xm, Sv_xp);
-    x_neighbours<VEC>(Sw_c, hSw, lane, x0, g.w, Sw_xm, Sw_xp);
-    x_neighbours<VEC>(ph_c, hph, lane, x0, g.w, ph_xm, ph_xp);
+    x_neighbours<VEC>(Su_c, hSu, lm.left_edge, lm.right_edge, x0, g.w, Su_xm, Su_xp);
+    x_neighbours<VEC>(Sv_c, hSv, lm.left_edge, lm.right_edge, x0, g.w, Sv_xm, Sv_xp);
+    x_neighbours<VEC>(Sw_c, hSw, lm.left_edge, lm.right_edge, x0, g.w, Sw_xm, Sw_xp);
+    x_neighbours<VEC>(ph_c, hph, lm.left_edge, lm.right_edge, x0, g.w, ph_xm, ph_xp);
 
     const int zg = g.z0g + z;  // faces are the GLOBAL ones when the level is sharded
     const float wzp = (zg < g.dg - 1) ? hz2 : 0.f;
@@ -310,10 +337,24 @@ __global__ void __launch_bounds__(128) sweep_kernel(const SweepArgs a) {
   }
 }
 
-static void pick_grid(const Dims& g, ZRange zr, int vec, int rows_per_block, dim3& grid, dim3& block, int& zchunk) {
+// lanes per row segment: the power of two in {32,16,8} that wastes the fewest lanes for this width
+static int pick_lpr(int w, int vec) {
+  int best = 32;
+  long long best_cols = -1;
+  for (int lpr = 32; lpr >= 8; lpr >>= 1) {
+    const int tile = lpr * vec;
+    const long long cols = (long long)((w + tile - 1) / tile) * tile;
+    if (best_cols < 0 || cols < best_cols) { best = lpr; best_cols = cols; }
+  }
+  return best;
+}
+
+static void pick_grid(const Dims& g, ZRange zr, int vec, int lpr, int warps_per_block, dim3& grid, dim3& block,
+                      int& zchunk) {
   const int nz = zr.end - zr.begin;
-  block = dim3(32, rows_per_block, 1);
-  const int gx = (g.w + 32 * vec - 1) / (32 * vec);
+  block = dim3(32, warps_per_block, 1);
+  const int rows_per_block = warps_per_block * (32 / lpr);
+  const int gx = (g.w + lpr * vec - 1) / (lpr * vec);
   const int gy = (g.h + rows_per_block - 1) / rows_per_block;
   // enough z chunks for >= ~8 CTAs per SM in flight, but chunks of at least 8 planes (each chunk
   // re-reads two planes of prologue)
@@ -352,9 +393,11 @@ int launch_sweep(const float* fx, const float* fy, const float* fz, const float*
   const int vec = pick_vec(g);
   static const int pf = env_int("FLOW3D_SWEEP_PF", 2);
   static const int rows = env_int("FLOW3D_SWEEP_ROWS", 4);
+  static const int forced_lpr = env_int("FLOW3D_LPR", 0);
   a.pf = pf;
+  a.lpr = (forced_lpr == 8 || forced_lpr == 16 || forced_lpr == 32) ? forced_lpr : pick_lpr(g.w, vec);
   dim3 grid, block;
-  pick_grid(g, zr, vec, rows, grid, block, a.zchunk);
+  pick_grid(g, zr, vec, a.lpr, rows, grid, block, a.zchunk);
   static const int unroll = env_int("FLOW3D_SWEEP_UNROLL", 1);
   if (unroll == 3) {
     if (vec == 4) sweep_kernel<4, 3><<<grid, block, 0, st>>>(a);
@@ -397,18 +440,18 @@ __device__ __forceinline__ float cdiff_r(float fp, float fm, float dfp, float df
 // stencil fields (u,du,v,dv,w,dw) register-rotated in z, x neighbours by shuffle, y neighbours from
 // the adjacent rows through L1.
 template <int VEC>
-__global__ void __launch_bounds__(128) phi_ksi_kernel(const PhiKsiArgs a, int zchunk, int pf, int zs, int ze) {
+__global__ void __launch_bounds__(128) phi_ksi_kernel(const PhiKsiArgs a, int zchunk, int pf, int zs, int ze,
+                                                      int lpr) {
   const Dims g = a.g;
-  const int lane = threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (y >= g.h) return;
-  const int x0_raw = (blockIdx.x * 32 + lane) * VEC;
-  const bool active = x0_raw < g.w;
-  const int x0 = active ? x0_raw : ((g.w - 1) / VEC) * VEC;
+  const LaneMap lm = lane_map<VEC>(lpr, g.w, g.h);
+  if ((int)((blockIdx.y * blockDim.y + threadIdx.y) * (32 / lpr)) >= g.h) return;
+  const int y = lm.y;
+  const bool active = lm.active;
+  const int x0 = lm.x0;
   const int z_begin = zs + blockIdx.z * zchunk;
   const int z_end = min(ze, z_begin + zchunk);
   if (z_begin >= z_end) return;
-  const int xh = (lane == 0) ? mirror_idx(x0 - 1, g.w) : ((lane == 31) ? mirror_idx(x0 + VEC, g.w) : x0);
+  const int xh = lm.left_edge ? mirror_idx(x0 - 1, g.w) : (lm.right_edge ? mirror_idx(x0 + VEC, g.w) : x0);
   const unsigned ps = (unsigned)g.ps;
   const unsigned row_c = (unsigned)y * g.ld + x0;
   const unsigned row_m = (unsigned)mirror_idx(y - 1, g.h) * g.ld + x0;
@@ -460,7 +503,7 @@ __global__ void __launch_bounds__(128) phi_ksi_kernel(const PhiKsiArgs a, int zc
       for (int f = 0; f < 6; ++f) halo[f] = __ldg(F[f] + oh);
     }
 #pragma unroll
-    for (int f = 0; f < 6; ++f) x_neighbours<VEC>(cur[f], halo[f], lane, x0, g.w, xm[f], xp[f]);
+    for (int f = 0; f < 6; ++f) x_neighbours<VEC>(cur[f], halo[f], lm.left_edge, lm.right_edge, x0, g.w, xm[f], xp[f]);
 
     Vec<VEC> ophi, oksi;
 #pragma unroll
@@ -527,10 +570,12 @@ int launch_phi_ksi(const float* fx, const float* fy, const float* fz, const floa
   if (forced == 1 || forced == 2 || forced == 4) vec = forced;
   dim3 grid, block;
   int zchunk = 0;
-  pick_grid(g, zr, vec, 4, grid, block, zchunk);
-  if (vec == 4) phi_ksi_kernel<4><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end);
-  else if (vec == 2) phi_ksi_kernel<2><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end);
-  else phi_ksi_kernel<1><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end);
+  static const int forced_lpr = env_int("FLOW3D_LPR", 0);
+  const int lpr = (forced_lpr == 8 || forced_lpr == 16 || forced_lpr == 32) ? forced_lpr : pick_lpr(g.w, vec);
+  pick_grid(g, zr, vec, lpr, 4, grid, block, zchunk);
+  if (vec == 4) phi_ksi_kernel<4><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end, lpr);
+  else if (vec == 2) phi_ksi_kernel<2><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end, lpr);
+  else phi_ksi_kernel<1><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end, lpr);
   count_launch();
   return check_launch("phi_ksi_kernel");
 }

@@ -271,6 +271,8 @@ class ShardedFlowSolver:
         self.min_planes = min_planes_per_rank
         self.min_voxels = min_voxels_per_rank
         self.stats = {"sharded_levels": 0, "replicated_levels": 0, "exchanges": 0, "exchange_bytes": 0}
+        self.profile = False      # record CUDA events around every batch of sweeps (CabiBackend only)
+        self.sweep_events = []    # (start, end, voxel_sweeps)
 
     # ---- neighbour exchange of ghost planes -------------------------------------------------------
     def _exchange(self, fields, A, B, a, b, H, D):
@@ -300,20 +302,27 @@ class ShardedFlowSolver:
         return per >= max(self.min_planes, 2 * H) and w * h * per >= self.min_voxels
 
     # ---- the solve ---------------------------------------------------------------------------------
-    def compute(self, frame_0, frame_1, params=None, level_cb=None):
-        """frame_0/frame_1: FULL volumes (numpy (D,H,W)) given to every rank.  Returns (a, b, [u,v,w]):
-        this rank's owned plane range of the finest level and numpy arrays of those planes (the full
-        volume on every rank if the finest level was too small to shard)."""
-        from .api import level_schedule
+    def compute(self, frame_0, frame_1, params=None, level_cb=None, width=None, return_device=False):
+        """frame_0/frame_1: FULL volumes given to every rank: numpy (D,H,W) arrays, or backend tensors
+        (D,H,ld) already on the device together with `width`.  Returns (a, b, [u,v,w]): this rank's owned
+        plane range of the finest level and those planes (numpy, or device tensors (b-a,H,ld) when
+        return_device) -- the full volume on every rank if the finest level was too small to shard."""
         be = self.be
         P = dict(DEFAULTS)
         P.update(params or {})
-        D, Hh, W = frame_0.shape
         inner, outer = int(P["inner_iterations_count"]), int(P["outer_iterations_count"])
         H = inner + 1
+        if isinstance(frame_0, np.ndarray):
+            D, Hh, W = frame_0.shape
+            F0 = be.from_numpy_full(frame_0)
+            F1 = be.from_numpy_full(frame_1)
+        else:
+            D, Hh, _ = frame_0.shape
+            W = int(width)
+            be.w_full = W
+            F0, F1 = frame_0, frame_1
         sched = self._schedule(W, Hh, D, P)
-        F0 = be.from_numpy_full(frame_0)
-        F1 = be.from_numpy_full(frame_1)
+        prof = self.profile
         if P["gaussian_sigma"] > 0:
             F0, F1 = be.blur(F0, P["gaussian_sigma"]), be.blur(F1, P["gaussian_sigma"])
         fullF0 = Slab(F0, 0, D, W)
@@ -358,11 +367,21 @@ class ShardedFlowSolver:
             for _ in range(outer):
                 be.phi_ksi(terms, flow[0], flow[1], flow[2], d_cur[0], d_cur[1], d_cur[2], h, P["equation_smoothness"],
                            P["equation_data"], phi, ksi, lo1, hi1)
+                if prof:
+                    e0 = torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    units = 0
                 for j in range(1, inner + 1):
                     lo = A if A == 0 else A + 1 + j
                     hi = B if B == d else B - 1 - j
                     be.sweep(terms, flow[0], flow[1], flow[2], d_cur, phi, ksi, h, P["equation_alpha"], d_alt, lo, hi)
                     d_cur, d_alt = d_alt, d_cur
+                    if prof:
+                        units += w * hh * (hi - lo)
+                if prof:
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    e1.record()
+                    self.sweep_events.append((e0, e1, units))
                 if sharded:
                     self._exchange(d_cur, A, B, a, b, H, d)
             # ---- u += du (:420-438), valid on the whole buffer because the last exchange refreshed du ----
@@ -381,7 +400,16 @@ class ShardedFlowSolver:
                 level_cb(level, dims, (a, b), [be.to_numpy(f.planes(a, b), w) for f in flow])
         dims, flow, _, _ = prev
         a, b = own_range(dims[2], self.rank, self.world) if self._is_sharded(dims, H) else (0, dims[2])
+        if return_device:
+            return a, b, [f.planes(a, b) for f in flow]
         return a, b, [be.to_numpy(f.planes(a, b), dims[0]) for f in flow]
+
+    def sweep_profile(self):
+        """(milliseconds, voxel-sweeps) accumulated by the recorded sweep batches; clears the record"""
+        ms = sum(e0.elapsed_time(e1) for e0, e1, _ in self.sweep_events)
+        units = sum(u for _, _, u in self.sweep_events)
+        self.sweep_events = []
+        return ms, units
 
     def _frame(self, full, full_whd, dims, lo, hi):
         """planes [lo, hi) of a level frame, box-resampled from the replicated full-resolution frame

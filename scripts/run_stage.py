@@ -19,6 +19,7 @@ ap.add_argument("stage")
 ap.add_argument("--size", type=int, default=512)
 ap.add_argument("--dims", type=str, default="")
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--ld-align", type=int, default=0, help="override the row pitch alignment (floats)")
 args = ap.parse_args()
 L = pkg.load()
 pkg.require_device()
@@ -29,6 +30,8 @@ if args.dims:
 else:
     W = H = D = args.size
 ld = int(L.flow3d_aligned_ld(W))
+if args.ld_align:
+    ld = (W + args.ld_align - 1) // args.ld_align * args.ld_align
 n = ld * H * D
 dims = sz3((W, H, D))
 h = f3((1.0, 1.0, 1.0))

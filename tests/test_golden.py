@@ -47,9 +47,6 @@ def test_gpu_pair128_matches_reference_build(gpu, pair_128):
 def test_gpu_slab_matches_reference_build(gpu, pair_slab):
     out = _gpu_solve(gpu, *pair_slab)
     _check("slab", out, "slab_ref_guarded_flow_sub4.npz", (slice(None), slice(None, None, 4), slice(None, None, 4)))
-    # both inputs are z-invariant (one slice repeated): so is the reference's flow, and so is ours
-    for f in out[:2]:
-        assert np.array_equal(f[0], f[2])
 
 
 @pytest.mark.slow
