@@ -63,6 +63,9 @@ __device__ __forceinline__ void stv(float* p, const Vec<VEC>& r) {
 __device__ __forceinline__ void prefetch_l2(const float* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
+__device__ __forceinline__ void prefetch_l1(const float* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
 
 template <int VEC>
 __device__ __forceinline__ Vec<VEC> addv(const Vec<VEC>& a, const Vec<VEC>& b) {
@@ -87,6 +90,7 @@ struct SweepArgs {
   int pf;  // prefetch distance in planes (0 = off)
   int zs, ze;  // compute range (local planes)
   int lpr;     // lanes per row segment (32, 16 or 8)
+  int pf1;     // L1 prefetch of the next plane (0 = off)
 };
 
 // Lane layout: a warp covers 32/lpr consecutive rows x (lpr*VEC) columns (lpr = lanes per row, a power
@@ -142,8 +146,8 @@ __device__ __forceinline__ void x_neighbours(const Vec<VEC>& c, float halo, bool
 // S = u + du (one rounded add per voxel, shared by all six consumers of that voxel) and phi are
 // register-rotated along z; y neighbours are read straight from global memory (L1-resident: they
 // are the centre rows of the adjacent warps of the same CTA).
-template <int VEC, int UNROLL>
-__global__ void __launch_bounds__(128) sweep_kernel(const SweepArgs a) {
+template <int VEC, int UNROLL, int MINB>
+__global__ void __launch_bounds__(128, MINB) sweep_kernel(const SweepArgs a) {
   const Dims g = a.g;
   const LaneMap lm = lane_map<VEC>(a.lpr, g.w, g.h);
   if ((int)((blockIdx.y * blockDim.y + threadIdx.y) * (32 / a.lpr)) >= g.h) return;  // whole warp leaves together
@@ -203,6 +207,21 @@ __global__ void __launch_bounds__(128) sweep_kernel(const SweepArgs a) {
 #pragma unroll UNROLL
   for (int z = z_begin; z < z_end; ++z) {
     const unsigned pl = (unsigned)z * ps;
+    if (a.pf1 > 0) {  // L1 prefetch of what the next iteration loads
+      const int zq1 = z + 2;
+      if (zq1 < g.d) {
+        const unsigned o = (unsigned)zq1 * ps + row_c;
+        prefetch_l1(a.u + o); prefetch_l1(a.v + o); prefetch_l1(a.w + o);
+        prefetch_l1(a.du + o); prefetch_l1(a.dv + o); prefetch_l1(a.dw + o);
+        prefetch_l1(a.phi + o);
+      }
+      const int zq0 = z + 1;
+      if (zq0 < g.d) {
+        const unsigned o = (unsigned)zq0 * ps + row_c;
+        prefetch_l1(a.fx + o); prefetch_l1(a.fy + o); prefetch_l1(a.fz + o);
+        prefetch_l1(a.ft + o); prefetch_l1(a.ksi + o);
+      }
+    }
     if (a.pf > 0) {
       const int zp1 = z + 1 + a.pf;  // stencil fields are consumed one plane ahead
       if (zp1 < g.d) {
@@ -389,24 +408,28 @@ int launch_sweep(const float* fx, const float* fy, const float* fz, const float*
                  float hy, float hz, float alpha, float* odu, float* odv, float* odw, cudaStream_t st) {
   if (zr.end <= zr.begin) return FLOW3D_OK;
   SweepArgs a{fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, odu, odv, odw, g, hx, hy, hz, alpha, 0, 0,
-              zr.begin, zr.end};
+              zr.begin, zr.end, 32, 0};
   const int vec = pick_vec(g);
   static const int pf = env_int("FLOW3D_SWEEP_PF", 2);
   static const int rows = env_int("FLOW3D_SWEEP_ROWS", 4);
   static const int forced_lpr = env_int("FLOW3D_LPR", 0);
   a.pf = pf;
+  static const int pf1 = env_int("FLOW3D_SWEEP_PF1", 0);
+  a.pf1 = pf1;
   a.lpr = (forced_lpr == 8 || forced_lpr == 16 || forced_lpr == 32) ? forced_lpr : pick_lpr(g.w, vec);
   dim3 grid, block;
   pick_grid(g, zr, vec, a.lpr, rows, grid, block, a.zchunk);
   static const int unroll = env_int("FLOW3D_SWEEP_UNROLL", 1);
-  if (unroll == 3) {
-    if (vec == 4) sweep_kernel<4, 3><<<grid, block, 0, st>>>(a);
-    else if (vec == 2) sweep_kernel<2, 3><<<grid, block, 0, st>>>(a);
-    else sweep_kernel<1, 3><<<grid, block, 0, st>>>(a);
+  static const int minb = env_int("FLOW3D_SWEEP_MINB", 2);
+  (void)unroll;
+  if (vec == 4) {
+    if (minb == 3) sweep_kernel<4, 1, 3><<<grid, block, 0, st>>>(a);
+    else if (minb == 4) sweep_kernel<4, 1, 4><<<grid, block, 0, st>>>(a);
+    else sweep_kernel<4, 1, 2><<<grid, block, 0, st>>>(a);
+  } else if (vec == 2) {
+    sweep_kernel<2, 1, 4><<<grid, block, 0, st>>>(a);
   } else {
-    if (vec == 4) sweep_kernel<4, 1><<<grid, block, 0, st>>>(a);
-    else if (vec == 2) sweep_kernel<2, 1><<<grid, block, 0, st>>>(a);
-    else sweep_kernel<1, 1><<<grid, block, 0, st>>>(a);
+    sweep_kernel<1, 1, 4><<<grid, block, 0, st>>>(a);
   }
   count_launch();
   return check_launch("sweep_kernel");
@@ -432,8 +455,8 @@ __device__ __forceinline__ float cdiff(const float* __restrict__ f, const float*
 }
 
 // value of ((f[p]-f[m]) + df[p]) - df[m]) / (2h) from already-loaded neighbours
-__device__ __forceinline__ float cdiff_r(float fp, float fm, float dfp, float dfm, float two_h) {
-  return __fdiv_rn(__fsub_rn(__fadd_rn(__fsub_rn(fp, fm), dfp), dfm), two_h);
+__device__ __forceinline__ float cdiff_r(float fp, float fm, float dfp, float dfm, ConstDiv two_h) {
+  return div_const(__fsub_rn(__fadd_rn(__fsub_rn(fp, fm), dfp), dfm), two_h);
 }
 
 // Same structure as the sweep: one warp per row segment of 32*VEC voxels marching along z, the six
@@ -457,7 +480,9 @@ __global__ void __launch_bounds__(128) phi_ksi_kernel(const PhiKsiArgs a, int zc
   const unsigned row_m = (unsigned)mirror_idx(y - 1, g.h) * g.ld + x0;
   const unsigned row_p = (unsigned)mirror_idx(y + 1, g.h) * g.ld + x0;
   const unsigned row_h = (unsigned)y * g.ld + xh;
-  const float thx = __fadd_rn(a.hx, a.hx), thy = __fadd_rn(a.hy, a.hy), thz = __fadd_rn(a.hz, a.hz);
+  // divisors 2h are loop invariants: exact division through the double reciprocal (common.cuh)
+  const ConstDiv thx = make_const_div(__fadd_rn(a.hx, a.hx)), thy = make_const_div(__fadd_rn(a.hy, a.hy)),
+                 thz = make_const_div(__fadd_rn(a.hz, a.hz));
 
   const float* F[6] = {a.u, a.du, a.v, a.dv, a.w, a.dw};
   Vec<VEC> prev[6], cur[6];

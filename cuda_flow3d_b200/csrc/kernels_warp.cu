@@ -97,8 +97,8 @@ int launch_warp(const float* f0, const float* f1, const float* u, const float* v
 }
 
 // fx = (((f0[p]-f0[m]) + f1w[p]) - f1w[m]) / (4h)   (solve_3d.cu:425-436), ft = f1w - f0 (:437-438)
-__device__ __forceinline__ float deriv(float a_p, float a_m, float b_p, float b_m, float four_h) {
-  return __fdiv_rn(__fsub_rn(__fadd_rn(__fsub_rn(a_p, a_m), b_p), b_m), four_h);
+__device__ __forceinline__ float deriv(float a_p, float a_m, float b_p, float b_m, ConstDiv four_h) {
+  return div_const(__fsub_rn(__fadd_rn(__fsub_rn(a_p, a_m), b_p), b_m), four_h);
 }
 
 __global__ void __launch_bounds__(256) derivatives_kernel(const float* __restrict__ f0,
@@ -120,9 +120,9 @@ __global__ void __launch_bounds__(256) derivatives_kernel(const float* __restric
   const long long cb = (long long)y * g.ld + x;
   const long long izp = cb + (long long)z_neighbour(g, z, 1) * g.ps;
   const long long izm = cb + (long long)z_neighbour(g, z, -1) * g.ps;
-  fx[c] = deriv(__ldg(f0 + ixp), __ldg(f0 + ixm), __ldg(f1w + ixp), __ldg(f1w + ixm), __fmul_rn(hx, 4.f));
-  fy[c] = deriv(__ldg(f0 + iyp), __ldg(f0 + iym), __ldg(f1w + iyp), __ldg(f1w + iym), __fmul_rn(hy, 4.f));
-  fz[c] = deriv(__ldg(f0 + izp), __ldg(f0 + izm), __ldg(f1w + izp), __ldg(f1w + izm), __fmul_rn(hz, 4.f));
+  fx[c] = deriv(__ldg(f0 + ixp), __ldg(f0 + ixm), __ldg(f1w + ixp), __ldg(f1w + ixm), make_const_div(__fmul_rn(hx, 4.f)));
+  fy[c] = deriv(__ldg(f0 + iyp), __ldg(f0 + iym), __ldg(f1w + iyp), __ldg(f1w + iym), make_const_div(__fmul_rn(hy, 4.f)));
+  fz[c] = deriv(__ldg(f0 + izp), __ldg(f0 + izm), __ldg(f1w + izp), __ldg(f1w + izm), make_const_div(__fmul_rn(hz, 4.f)));
   ft[c] = __fsub_rn(__ldg(f1w + c), __ldg(f0 + c));
 }
 
@@ -155,7 +155,8 @@ __global__ void __launch_bounds__(WD_TX* WD_TY) warp_derivatives_kernel(
   const int z_end = min(ze, z_begin + zchunk);
   if (z_begin >= z_end) return;
   const bool valid = (x < g.w) && (y < g.h);
-  const float fhx = __fmul_rn(hx, 4.f), fhy = __fmul_rn(hy, 4.f), fhz = __fmul_rn(hz, 4.f);
+  const ConstDiv fhx = make_const_div(__fmul_rn(hx, 4.f)), fhy = make_const_div(__fmul_rn(hy, 4.f)),
+                 fhz = make_const_div(__fmul_rn(hz, 4.f));
   constexpr int CELLS = (WD_TY + 2) * (WD_TX + 2);
 
   // fill ring slot `slot` with the warped plane mirror(zz): cell (r,cx) <-> voxel
