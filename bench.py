@@ -238,7 +238,7 @@ def run_sharded(args, rank, world, local_rank):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
     value = (W * H * D) / (ms_per_step / 1000.0) / 1e6
-    sw_ms, sw_units = solver.sweep_profile()
+    sw_ms, sw_units, phi_units = solver.sweep_profile()
     solver.profile = False
     stats = dict(solver.stats)
 
@@ -270,7 +270,7 @@ def run_sharded(args, rank, world, local_rank):
                "note": "per rank: both full frames up (replicated), own z-shard of the flow down"}
     if rank == 0:
         peak, peak_src = hbm_peak()
-        achieved = SWEEP_BYTES * sw_units / (sw_ms / 1000.0) / 1e9 if sw_ms > 0 else 0.0
+        achieved = (SWEEP_BYTES * sw_units + PHIKSI_BYTES * phi_units) / (sw_ms / 1000.0) / 1e9 if sw_ms > 0 else 0.0
         nsum, nlev = level_voxel_sum(pkg, W, H, D, P)
         line = {
             "metric": "Mvoxel/s per full pyramid flow solve", "value": value, "unit": "Mvoxel/s",
@@ -286,10 +286,12 @@ def run_sharded(args, rank, world, local_rank):
                        "halo_bytes_sent_per_step_rank0": stats["exchange_bytes"] / max(1, args.steps),
                        "parity": "bit-identical to the single-GPU solve (tests/test_dist_gpu.py)"},
             "clocks": clocks, "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "sweep_kernel (rank 0, its z-slab incl. ghost planes)",
+            "roofline": {"bound": "hbm", "kernel": "solver outer iterations on rank 0 (1 phi_ksi_kernel + 5 sweep_kernel "
+                                                    "launches each, on its z-slab incl. ghost planes)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_voxel_sweep": SWEEP_BYTES,
-                         "voxel_sweeps": sw_units, "traffic": None},
+                         "algorithmic_bytes_per_phi_ksi_voxel": PHIKSI_BYTES,
+                         "voxel_sweeps": sw_units, "phi_ksi_voxels": phi_units, "traffic": None},
         }
         if e2e:
             line["e2e"] = e2e

@@ -624,6 +624,35 @@ int flow3d_warp_derivatives_slab(const float* f0, const float* f1, size_t f1_z0_
                                  h[0], h[1], h[2], fx, fy, fz, ft, S(stream));
 }
 
+int flow3d_outer_iteration_slab(const float* fx, const float* fy, const float* fz, const float* ft,
+                                const float* u, const float* v, const float* w, float* du, float* dv,
+                                float* dw, float* tdu, float* tdv, float* tdw, float* phi, float* ksi,
+                                const size_t dims[3], size_t ld, const flow3d_zslab* slab,
+                                const float h[3], size_t inner, float alpha, float eps_smooth,
+                                float eps_data, int* result_in_tmp, void* stream) {
+  const void* ps[] = {fx, fy, fz, ft, u, v, w, du, dv, dw, tdu, tdv, tdw, phi, ksi};
+  for (const void* p : ps) F3D_TRY(check_volume(p, dims, ld));
+  F3D_TRY(check_slab(dims, slab));
+  if (!h || !slab || !result_in_tmp) return FLOW3D_ERR_INVALID_ARG;
+  const Dims g = make_slab_dims(dims, ld, slab);
+  const ZRange r0 = make_range(g, slab);
+  const bool lo_face = (g.z0g + r0.begin) == 0, hi_face = (g.z0g + r0.end) == g.dg;
+  cudaStream_t st = S(stream);
+  F3D_TRY(launch_phi_ksi(fx, fy, fz, ft, u, v, w, du, dv, dw, g, r0, h[0], h[1], h[2], eps_smooth, eps_data, phi,
+                         ksi, st));
+  float *a0 = du, *a1 = dv, *a2 = dw, *b0 = tdu, *b1 = tdv, *b2 = tdw;
+  for (size_t j = 1; j <= inner; ++j) {
+    ZRange r{lo_face ? r0.begin : r0.begin + (int)j, hi_face ? r0.end : r0.end - (int)j};
+    F3D_TRY(launch_sweep(fx, fy, fz, ft, u, v, w, a0, a1, a2, phi, ksi, g, r, h[0], h[1], h[2], alpha, b0, b1, b2,
+                         st));
+    std::swap(a0, b0);
+    std::swap(a1, b1);
+    std::swap(a2, b2);
+  }
+  *result_in_tmp = (a0 == tdu) ? 1 : 0;
+  return FLOW3D_OK;
+}
+
 int flow3d_median_slab(const float* in, float* out, const size_t dims[3], size_t ld,
                        const flow3d_zslab* slab, size_t radius, void* stream) {
   F3D_TRY(check_volume(in, dims, ld));

@@ -91,6 +91,7 @@ struct SweepArgs {
   int zs, ze;  // compute range (local planes)
   int lpr;     // lanes per row segment (32, 16 or 8)
   int pf1;     // L1 prefetch of the next plane (0 = off)
+  int wx;      // warps side by side along x within a block
 };
 
 // Lane layout: a warp covers 32/lpr consecutive rows x (lpr*VEC) columns (lpr = lanes per row, a power
@@ -102,17 +103,24 @@ struct LaneMap {
   bool active;     // false: idle lane (x beyond the volume), shadows the last group, stores nothing
   bool row_ok;     // false: row beyond the volume (idle, clamped to the last row)
   bool left_edge, right_edge;
+  int tile_x, first_row;  // this warp's x tile index and first row
 };
+// wx = warps of a block placed side by side along x (the rest stack along y): wx > 1 makes a block
+// read longer contiguous runs of every row
 template <int VEC>
-__device__ __forceinline__ LaneMap lane_map(int lpr, int w, int h) {
+__device__ __forceinline__ LaneMap lane_map(int lpr, int w, int h, int wx = 1) {
   LaneMap m;
   const int lane = threadIdx.x;
   m.sub = lane & (lpr - 1);
   const int rows_per_warp = 32 / lpr;
-  const int y_raw = (blockIdx.y * blockDim.y + threadIdx.y) * rows_per_warp + lane / lpr;
+  const int warp_x = threadIdx.y % wx, warp_y = threadIdx.y / wx;
+  const int wy = blockDim.y / wx;
+  m.tile_x = blockIdx.x * wx + warp_x;
+  m.first_row = (blockIdx.y * wy + warp_y) * rows_per_warp;
+  const int y_raw = m.first_row + lane / lpr;
   m.row_ok = y_raw < h;
   m.y = m.row_ok ? y_raw : h - 1;
-  const int x0_raw = (blockIdx.x * lpr + m.sub) * VEC;
+  const int x0_raw = (m.tile_x * lpr + m.sub) * VEC;
   m.active = (x0_raw < w) && m.row_ok;
   m.x0 = (x0_raw < w) ? x0_raw : ((w - 1) / VEC) * VEC;
   m.left_edge = m.sub == 0;
@@ -142,217 +150,265 @@ __device__ __forceinline__ void x_neighbours(const Vec<VEC>& c, float halo, bool
   }
 }
 
-// Each warp owns one row segment of 32*VEC voxels and marches through a chunk of z planes.
-// S = u + du (one rounded add per voxel, shared by all six consumers of that voxel) and phi are
-// register-rotated along z; y neighbours are read straight from global memory (L1-resident: they
-// are the centre rows of the adjacent warps of the same CTA).
-template <int VEC, int UNROLL, int MINB>
+// Each warp owns 32/lpr row segments of lpr*VEC voxels and marches through a chunk of z planes.
+// S = u + du (one rounded add per voxel, shared by all six consumers of that voxel) and phi are kept
+// in registers for three consecutive planes; y neighbours are read straight from global memory
+// (L1-resident: they are the centre rows of the adjacent warps of the same CTA).
+//
+// The three planes live in three register sets whose ROLES (previous / current / next) rotate through
+// an explicitly 3x-unrolled loop, so the rotation costs no register moves; and the plane body is
+// compiled twice, for warps whose tile touches an x face of the volume (EDGE: mirror selects, zeroed
+// face weights) and for interior warps (no selects at all).
+template <int VEC>
+struct PlaneRegs {
+  Vec<VEC> Su, Sv, Sw, ph;  // live while the plane is next / current / previous
+  Vec<VEC> u, v, w, dv, dw; // live while the plane is next / current
+};
+
+template <int VEC>
+struct SweepCtx {
+  unsigned ps, row_c, row_m, row_p, row_h;
+  float hx2, hz2, wyp, wym;
+  int x0, w;
+  bool left_edge, right_edge, active;
+};
+
+template <int VEC>
+__device__ __forceinline__ void load_plane(const SweepArgs& a, unsigned o, PlaneRegs<VEC>& r) {
+  r.u = ldv<VEC>(a.u + o);
+  r.v = ldv<VEC>(a.v + o);
+  r.w = ldv<VEC>(a.w + o);
+  const Vec<VEC> du = ldv<VEC>(a.du + o);
+  r.dv = ldv<VEC>(a.dv + o);
+  r.dw = ldv<VEC>(a.dw + o);
+  r.ph = ldv<VEC>(a.phi + o);
+  r.Su = addv<VEC>(r.u, du);
+  r.Sv = addv<VEC>(r.v, r.dv);
+  r.Sw = addv<VEC>(r.w, r.dw);
+}
+
+// x neighbours of an interior tile: no volume face inside the warp's tile, plain shuffles + halo
+template <int VEC>
+__device__ __forceinline__ void x_neighbours_interior(const Vec<VEC>& c, float halo, bool left_edge,
+                                                      bool right_edge, Vec<VEC>& left, Vec<VEC>& right) {
+  float from_left = __shfl_up_sync(0xffffffffu, c.v[VEC - 1], 1);
+  float from_right = __shfl_down_sync(0xffffffffu, c.v[0], 1);
+  if (left_edge) from_left = halo;
+  if (right_edge) from_right = halo;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    left.v[i] = (i > 0) ? c.v[i - 1] : from_left;
+    right.v[i] = (i < VEC - 1) ? c.v[i + 1] : from_right;
+  }
+}
+
+// one plane of the sweep: P = previous plane, C = current, N = receives plane z+1
+template <int VEC, bool EDGE>
+__device__ __forceinline__ void sweep_plane(const SweepArgs& a, const Dims& g, const SweepCtx<VEC>& c, int z,
+                                            const PlaneRegs<VEC>& P, const PlaneRegs<VEC>& C, PlaneRegs<VEC>& N) {
+  const unsigned ps = c.ps;
+  const unsigned pl = (unsigned)z * ps;
+  if (a.pf > 0) {
+    const int zp1 = z + 1 + a.pf;  // stencil fields are consumed one plane ahead
+    if (zp1 < g.d) {
+      const unsigned o = (unsigned)zp1 * ps + c.row_c;
+      prefetch_l2(a.u + o); prefetch_l2(a.v + o); prefetch_l2(a.w + o);
+      prefetch_l2(a.du + o); prefetch_l2(a.dv + o); prefetch_l2(a.dw + o);
+      prefetch_l2(a.phi + o);
+    }
+    const int zp0 = z + a.pf;
+    if (zp0 < g.d) {
+      const unsigned o = (unsigned)zp0 * ps + c.row_c;
+      prefetch_l2(a.fx + o); prefetch_l2(a.fy + o); prefetch_l2(a.fz + o);
+      prefetch_l2(a.ft + o); prefetch_l2(a.ksi + o);
+    }
+  }
+  // ---- next plane (reflect at the rear face) --------------------------------------------------
+  load_plane<VEC>(a, (unsigned)z_neighbour(g, z, 1) * ps + c.row_c, N);
+  // ---- centre-only fields of the current plane ------------------------------------------------
+  const unsigned oc = pl + c.row_c;
+  const Vec<VEC> fx = ldv<VEC>(a.fx + oc);
+  const Vec<VEC> fy = ldv<VEC>(a.fy + oc);
+  const Vec<VEC> fz = ldv<VEC>(a.fz + oc);
+  const Vec<VEC> ft = ldv<VEC>(a.ft + oc);
+  const Vec<VEC> ks = ldv<VEC>(a.ksi + oc);
+  // ---- y neighbours of the current plane -------------------------------------------------------
+  const unsigned om = pl + c.row_m;
+  const unsigned op = pl + c.row_p;
+  const Vec<VEC> Su_ym = addv<VEC>(ldv<VEC>(a.u + om), ldv<VEC>(a.du + om));
+  const Vec<VEC> Sv_ym = addv<VEC>(ldv<VEC>(a.v + om), ldv<VEC>(a.dv + om));
+  const Vec<VEC> Sw_ym = addv<VEC>(ldv<VEC>(a.w + om), ldv<VEC>(a.dw + om));
+  const Vec<VEC> ph_ym = ldv<VEC>(a.phi + om);
+  const Vec<VEC> Su_yp = addv<VEC>(ldv<VEC>(a.u + op), ldv<VEC>(a.du + op));
+  const Vec<VEC> Sv_yp = addv<VEC>(ldv<VEC>(a.v + op), ldv<VEC>(a.dv + op));
+  const Vec<VEC> Sw_yp = addv<VEC>(ldv<VEC>(a.w + op), ldv<VEC>(a.dw + op));
+  const Vec<VEC> ph_yp = ldv<VEC>(a.phi + op);
+  // ---- x halo: every lane loads (no branch, so these loads are issued with the batch above: one
+  // memory round trip per plane); only the first / last lane of a row segment uses the value
+  const unsigned oh = pl + c.row_h;
+  const float hSu = __fadd_rn(__ldg(a.u + oh), __ldg(a.du + oh));
+  const float hSv = __fadd_rn(__ldg(a.v + oh), __ldg(a.dv + oh));
+  const float hSw = __fadd_rn(__ldg(a.w + oh), __ldg(a.dw + oh));
+  const float hph = __ldg(a.phi + oh);
+  Vec<VEC> Su_xm, Su_xp, Sv_xm, Sv_xp, Sw_xm, Sw_xp, ph_xm, ph_xp;
+  if constexpr (EDGE) {
+    x_neighbours<VEC>(C.Su, hSu, c.left_edge, c.right_edge, c.x0, c.w, Su_xm, Su_xp);
+    x_neighbours<VEC>(C.Sv, hSv, c.left_edge, c.right_edge, c.x0, c.w, Sv_xm, Sv_xp);
+    x_neighbours<VEC>(C.Sw, hSw, c.left_edge, c.right_edge, c.x0, c.w, Sw_xm, Sw_xp);
+    x_neighbours<VEC>(C.ph, hph, c.left_edge, c.right_edge, c.x0, c.w, ph_xm, ph_xp);
+  } else {
+    x_neighbours_interior<VEC>(C.Su, hSu, c.left_edge, c.right_edge, Su_xm, Su_xp);
+    x_neighbours_interior<VEC>(C.Sv, hSv, c.left_edge, c.right_edge, Sv_xm, Sv_xp);
+    x_neighbours_interior<VEC>(C.Sw, hSw, c.left_edge, c.right_edge, Sw_xm, Sw_xp);
+    x_neighbours_interior<VEC>(C.ph, hph, c.left_edge, c.right_edge, ph_xm, ph_xp);
+  }
+
+  const int zg = g.z0g + z;  // faces are the GLOBAL ones when the level is sharded
+  const float wzp = (zg < g.dg - 1) ? c.hz2 : 0.f;
+  const float wzm = (zg > 0) ? c.hz2 : 0.f;
+
+  Vec<VEC> rdu, rdv, rdw;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    float wxp = c.hx2, wxm = c.hx2;
+    if constexpr (EDGE) {
+      const int x = c.x0 + i;
+      wxp = (x < c.w - 1) ? c.hx2 : 0.f;
+      wxm = (x > 0) ? c.hx2 : 0.f;
+    }
+    const float J11 = __fmul_rn(fx.v[i], fx.v[i]);
+    const float J22 = __fmul_rn(fy.v[i], fy.v[i]);
+    const float J33 = __fmul_rn(fz.v[i], fz.v[i]);
+    const float J12 = __fmul_rn(fx.v[i], fy.v[i]);
+    const float J13 = __fmul_rn(fx.v[i], fz.v[i]);
+    const float J23 = __fmul_rn(fy.v[i], fz.v[i]);
+    const float J14 = __fmul_rn(fx.v[i], ft.v[i]);
+    const float J24 = __fmul_rn(fy.v[i], ft.v[i]);
+    const float J34 = __fmul_rn(fz.v[i], ft.v[i]);
+    const float pc = C.ph.v[i];
+    // face weights: w * (phi_n + phi_c)/2  (solve_3d.cu:462-469); plain products
+    const float axp = __fmul_rn(wxp, __fmul_rn(__fadd_rn(ph_xp.v[i], pc), 0.5f));
+    const float axm = __fmul_rn(wxm, __fmul_rn(__fadd_rn(ph_xm.v[i], pc), 0.5f));
+    const float ayp = __fmul_rn(c.wyp, __fmul_rn(__fadd_rn(ph_yp.v[i], pc), 0.5f));
+    const float aym = __fmul_rn(c.wym, __fmul_rn(__fadd_rn(ph_ym.v[i], pc), 0.5f));
+    const float azp = __fmul_rn(wzp, __fmul_rn(__fadd_rn(N.ph.v[i], pc), 0.5f));
+    const float azm = __fmul_rn(wzm, __fmul_rn(__fadd_rn(P.ph.v[i], pc), 0.5f));
+    const float sumH = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(axp, axm), ayp), aym), azp), azm);
+    const float uc = C.u.v[i], vc = C.v.v[i], wc = C.w.v[i];
+    // solve_3d.cu:470-490: seed with the rounded x- product, then one fma per face
+    float sumU = __fmul_rn(axm, __fsub_rn(Su_xm.v[i], uc));
+    sumU = __fmaf_rn(axp, __fsub_rn(Su_xp.v[i], uc), sumU);
+    sumU = __fmaf_rn(ayp, __fsub_rn(Su_yp.v[i], uc), sumU);
+    sumU = __fmaf_rn(aym, __fsub_rn(Su_ym.v[i], uc), sumU);
+    sumU = __fmaf_rn(azp, __fsub_rn(N.Su.v[i], uc), sumU);
+    sumU = __fmaf_rn(azm, __fsub_rn(P.Su.v[i], uc), sumU);
+    float sumV = __fmul_rn(axm, __fsub_rn(Sv_xm.v[i], vc));
+    sumV = __fmaf_rn(axp, __fsub_rn(Sv_xp.v[i], vc), sumV);
+    sumV = __fmaf_rn(ayp, __fsub_rn(Sv_yp.v[i], vc), sumV);
+    sumV = __fmaf_rn(aym, __fsub_rn(Sv_ym.v[i], vc), sumV);
+    sumV = __fmaf_rn(azp, __fsub_rn(N.Sv.v[i], vc), sumV);
+    sumV = __fmaf_rn(azm, __fsub_rn(P.Sv.v[i], vc), sumV);
+    float sumW = __fmul_rn(axm, __fsub_rn(Sw_xm.v[i], wc));
+    sumW = __fmaf_rn(axp, __fsub_rn(Sw_xp.v[i], wc), sumW);
+    sumW = __fmaf_rn(ayp, __fsub_rn(Sw_yp.v[i], wc), sumW);
+    sumW = __fmaf_rn(aym, __fsub_rn(Sw_ym.v[i], wc), sumW);
+    sumW = __fmaf_rn(azp, __fsub_rn(N.Sw.v[i], wc), sumW);
+    sumW = __fmaf_rn(azm, __fsub_rn(P.Sw.v[i], wc), sumW);
+    // solve_3d.cu:492-502; numerators as the reference's SASS evaluates them (ptxas contracts the
+    // PTX's mul+sub pairs): n = fma(-J13, dw, fma(-J12, dv, -J14))
+    const float k = ks.v[i];
+    const float ndu = __fmaf_rn(-J13, C.dw.v[i], __fmaf_rn(-J12, C.dv.v[i], -J14));
+    const float r_du = __fdiv_rn(__fmaf_rn(k, ndu, sumU), __fmaf_rn(J11, k, sumH));
+    const float ndv = __fmaf_rn(-J23, C.dw.v[i], __fmaf_rn(-J12, r_du, -J24));
+    const float r_dv = __fdiv_rn(__fmaf_rn(k, ndv, sumV), __fmaf_rn(J22, k, sumH));
+    const float ndw = __fmaf_rn(-J23, r_dv, __fmaf_rn(-J13, r_du, -J34));
+    const float r_dw = __fdiv_rn(__fmaf_rn(k, ndw, sumW), __fmaf_rn(J33, k, sumH));
+    rdu.v[i] = r_du;
+    rdv.v[i] = r_dv;
+    rdw.v[i] = r_dw;
+  }
+  if (c.active) {
+    stv<VEC>(a.odu + oc, rdu);
+    stv<VEC>(a.odv + oc, rdv);
+    stv<VEC>(a.odw + oc, rdw);
+  }
+}
+
+template <int VEC, bool EDGE>
+__device__ __forceinline__ void sweep_march(const SweepArgs& a, const Dims& g, const SweepCtx<VEC>& c, int z_begin,
+                                            int z_end) {
+  PlaneRegs<VEC> A, B, Cc;
+  // prologue: plane z_begin-1 (reflected at the front face) and plane z_begin
+  load_plane<VEC>(a, (unsigned)z_neighbour(g, z_begin, -1) * c.ps + c.row_c, A);
+  load_plane<VEC>(a, (unsigned)z_begin * c.ps + c.row_c, B);
+  for (int z = z_begin; z < z_end; z += 3) {
+    sweep_plane<VEC, EDGE>(a, g, c, z, A, B, Cc);
+    if (z + 1 >= z_end) break;
+    sweep_plane<VEC, EDGE>(a, g, c, z + 1, B, Cc, A);
+    if (z + 2 >= z_end) break;
+    sweep_plane<VEC, EDGE>(a, g, c, z + 2, Cc, A, B);
+  }
+}
+
+// single-body loop: the roles rotate by copying (the compiler turns most copies into renames)
+template <int VEC, bool EDGE>
+__device__ __forceinline__ void sweep_march1(const SweepArgs& a, const Dims& g, const SweepCtx<VEC>& c, int z_begin,
+                                             int z_end) {
+  PlaneRegs<VEC> P, C, N;
+  load_plane<VEC>(a, (unsigned)z_neighbour(g, z_begin, -1) * c.ps + c.row_c, P);
+  load_plane<VEC>(a, (unsigned)z_begin * c.ps + c.row_c, C);
+#pragma unroll 1
+  for (int z = z_begin; z < z_end; ++z) {
+    sweep_plane<VEC, EDGE>(a, g, c, z, P, C, N);
+    P.Su = C.Su; P.Sv = C.Sv; P.Sw = C.Sw; P.ph = C.ph;
+    C = N;
+  }
+}
+
+template <int VEC, int MINB, int ROT, int SPEC>
 __global__ void __launch_bounds__(128, MINB) sweep_kernel(const SweepArgs a) {
   const Dims g = a.g;
-  const LaneMap lm = lane_map<VEC>(a.lpr, g.w, g.h);
-  if ((int)((blockIdx.y * blockDim.y + threadIdx.y) * (32 / a.lpr)) >= g.h) return;  // whole warp leaves together
+  const LaneMap lm = lane_map<VEC>(a.lpr, g.w, g.h, a.wx);
+  if (lm.first_row >= g.h || lm.tile_x * a.lpr * VEC >= g.w) return;  // whole warp leaves together
   const int y = lm.y;
-  const bool active = lm.active;
   const int x0 = lm.x0;  // idle lanes shadow the last group / last row
   const int z_begin = a.zs + blockIdx.z * a.zchunk;
   const int z_end = min(a.ze, z_begin + a.zchunk);
   if (z_begin >= z_end) return;
 
-  const int ym = mirror_idx(y - 1, g.h);
-  const int yp = mirror_idx(y + 1, g.h);
   // halo column of this lane: first lane of a row segment -> x0-1, last -> x0+VEC (mirrored at the
   // faces); the other lanes re-read their own first element (an L1 hit) so the load needs no branch
   const int xh = lm.left_edge ? mirror_idx(x0 - 1, g.w) : (lm.right_edge ? mirror_idx(x0 + VEC, g.w) : x0);
 
+  SweepCtx<VEC> c;
   // 32-bit element offsets (volumes hold < 2^32 elements; checked by the launcher): one
   // IMAD.WIDE per load instead of a 64-bit add pair
-  const unsigned ps = (unsigned)g.ps;
-  const unsigned row_c = (unsigned)y * g.ld + x0;
-  const unsigned row_m = (unsigned)ym * g.ld + x0;
-  const unsigned row_p = (unsigned)yp * g.ld + x0;
-  const unsigned row_h = (unsigned)y * g.ld + xh;
-
+  c.ps = (unsigned)g.ps;
+  c.row_c = (unsigned)y * g.ld + x0;
+  c.row_m = (unsigned)mirror_idx(y - 1, g.h) * g.ld + x0;
+  c.row_p = (unsigned)mirror_idx(y + 1, g.h) * g.ld + x0;
+  c.row_h = (unsigned)y * g.ld + xh;
   // weights (solve_3d.cu:451-460): alpha / (h*h), zeroed at the volume faces
-  const float hx2 = __fdiv_rn(a.alpha, __fmul_rn(a.hx, a.hx));
+  c.hx2 = __fdiv_rn(a.alpha, __fmul_rn(a.hx, a.hx));
   const float hy2 = __fdiv_rn(a.alpha, __fmul_rn(a.hy, a.hy));
-  const float hz2 = __fdiv_rn(a.alpha, __fmul_rn(a.hz, a.hz));
-  const float wyp = (y < g.h - 1) ? hy2 : 0.f;
-  const float wym = (y > 0) ? hy2 : 0.f;
+  c.hz2 = __fdiv_rn(a.alpha, __fmul_rn(a.hz, a.hz));
+  c.wyp = (y < g.h - 1) ? hy2 : 0.f;
+  c.wym = (y > 0) ? hy2 : 0.f;
+  c.x0 = x0;
+  c.w = g.w;
+  c.left_edge = lm.left_edge;
+  c.right_edge = lm.right_edge;
+  c.active = lm.active;
 
-  // ---- prologue: planes mirror(z_begin-1) [prev] and z_begin [cur] --------------------------
-  Vec<VEC> Su_p, Sv_p, Sw_p, ph_p;  // previous plane: S and phi only
-  Vec<VEC> Su_c, Sv_c, Sw_c, ph_c;  // current plane
-  Vec<VEC> u_c, v_c, w_c, dv_c, dw_c;
-  {
-    const unsigned o = (unsigned)z_neighbour(g, z_begin, -1) * ps + row_c;
-    Su_p = addv<VEC>(ldv<VEC>(a.u + o), ldv<VEC>(a.du + o));
-    Sv_p = addv<VEC>(ldv<VEC>(a.v + o), ldv<VEC>(a.dv + o));
-    Sw_p = addv<VEC>(ldv<VEC>(a.w + o), ldv<VEC>(a.dw + o));
-    ph_p = ldv<VEC>(a.phi + o);
-  }
-  {
-    const unsigned o = (unsigned)z_begin * ps + row_c;
-    u_c = ldv<VEC>(a.u + o);
-    v_c = ldv<VEC>(a.v + o);
-    w_c = ldv<VEC>(a.w + o);
-    Vec<VEC> du_c = ldv<VEC>(a.du + o);
-    dv_c = ldv<VEC>(a.dv + o);
-    dw_c = ldv<VEC>(a.dw + o);
-    Su_c = addv<VEC>(u_c, du_c);
-    Sv_c = addv<VEC>(v_c, dv_c);
-    Sw_c = addv<VEC>(w_c, dw_c);
-    ph_c = ldv<VEC>(a.phi + o);
-  }
-
-#pragma unroll UNROLL
-  for (int z = z_begin; z < z_end; ++z) {
-    const unsigned pl = (unsigned)z * ps;
-    if (a.pf1 > 0) {  // L1 prefetch of what the next iteration loads
-      const int zq1 = z + 2;
-      if (zq1 < g.d) {
-        const unsigned o = (unsigned)zq1 * ps + row_c;
-        prefetch_l1(a.u + o); prefetch_l1(a.v + o); prefetch_l1(a.w + o);
-        prefetch_l1(a.du + o); prefetch_l1(a.dv + o); prefetch_l1(a.dw + o);
-        prefetch_l1(a.phi + o);
-      }
-      const int zq0 = z + 1;
-      if (zq0 < g.d) {
-        const unsigned o = (unsigned)zq0 * ps + row_c;
-        prefetch_l1(a.fx + o); prefetch_l1(a.fy + o); prefetch_l1(a.fz + o);
-        prefetch_l1(a.ft + o); prefetch_l1(a.ksi + o);
-      }
-    }
-    if (a.pf > 0) {
-      const int zp1 = z + 1 + a.pf;  // stencil fields are consumed one plane ahead
-      if (zp1 < g.d) {
-        const unsigned o = (unsigned)zp1 * ps + row_c;
-        prefetch_l2(a.u + o); prefetch_l2(a.v + o); prefetch_l2(a.w + o);
-        prefetch_l2(a.du + o); prefetch_l2(a.dv + o); prefetch_l2(a.dw + o);
-        prefetch_l2(a.phi + o);
-      }
-      const int zp0 = z + a.pf;
-      if (zp0 < g.d) {
-        const unsigned o = (unsigned)zp0 * ps + row_c;
-        prefetch_l2(a.fx + o); prefetch_l2(a.fy + o); prefetch_l2(a.fz + o);
-        prefetch_l2(a.ft + o); prefetch_l2(a.ksi + o);
-      }
-    }
-    // ---- next plane (reflect at the rear face) ------------------------------------------------
-    const unsigned on = (unsigned)z_neighbour(g, z, 1) * ps + row_c;
-    const Vec<VEC> u_n = ldv<VEC>(a.u + on);
-    const Vec<VEC> v_n = ldv<VEC>(a.v + on);
-    const Vec<VEC> w_n = ldv<VEC>(a.w + on);
-    const Vec<VEC> du_n = ldv<VEC>(a.du + on);
-    const Vec<VEC> dv_n = ldv<VEC>(a.dv + on);
-    const Vec<VEC> dw_n = ldv<VEC>(a.dw + on);
-    const Vec<VEC> ph_n = ldv<VEC>(a.phi + on);
-    const Vec<VEC> Su_n = addv<VEC>(u_n, du_n);
-    const Vec<VEC> Sv_n = addv<VEC>(v_n, dv_n);
-    const Vec<VEC> Sw_n = addv<VEC>(w_n, dw_n);
-    // ---- centre-only fields of the current plane ----------------------------------------------
-    const unsigned oc = pl + row_c;
-    const Vec<VEC> fx = ldv<VEC>(a.fx + oc);
-    const Vec<VEC> fy = ldv<VEC>(a.fy + oc);
-    const Vec<VEC> fz = ldv<VEC>(a.fz + oc);
-    const Vec<VEC> ft = ldv<VEC>(a.ft + oc);
-    const Vec<VEC> ks = ldv<VEC>(a.ksi + oc);
-    // ---- y neighbours of the current plane -----------------------------------------------------
-    const unsigned om = pl + row_m;
-    const unsigned op = pl + row_p;
-    const Vec<VEC> Su_ym = addv<VEC>(ldv<VEC>(a.u + om), ldv<VEC>(a.du + om));
-    const Vec<VEC> Sv_ym = addv<VEC>(ldv<VEC>(a.v + om), ldv<VEC>(a.dv + om));
-    const Vec<VEC> Sw_ym = addv<VEC>(ldv<VEC>(a.w + om), ldv<VEC>(a.dw + om));
-    const Vec<VEC> ph_ym = ldv<VEC>(a.phi + om);
-    const Vec<VEC> Su_yp = addv<VEC>(ldv<VEC>(a.u + op), ldv<VEC>(a.du + op));
-    const Vec<VEC> Sv_yp = addv<VEC>(ldv<VEC>(a.v + op), ldv<VEC>(a.dv + op));
-    const Vec<VEC> Sw_yp = addv<VEC>(ldv<VEC>(a.w + op), ldv<VEC>(a.dw + op));
-    const Vec<VEC> ph_yp = ldv<VEC>(a.phi + op);
-    // ---- x halo (two lanes per warp) -------------------------------------------------------------
-    // every lane loads (no branch, so the loads are issued together with the batch above and cost
-    // one memory round trip per plane instead of two); only lanes 0 / 31 use the value
-    const unsigned oh = pl + row_h;
-    const float hSu = __fadd_rn(__ldg(a.u + oh), __ldg(a.du + oh));
-    const float hSv = __fadd_rn(__ldg(a.v + oh), __ldg(a.dv + oh));
-    const float hSw = __fadd_rn(__ldg(a.w + oh), __ldg(a.dw + oh));
-    const float hph = __ldg(a.phi + oh);
-    Vec<VEC> Su_xm, Su_xp, Sv_xm, Sv_xp, Sw_xm, Sw_xp, ph_xm, ph_xp;
-    x_neighbours<VEC>(Su_c, hSu, lm.left_edge, lm.right_edge, x0, g.w, Su_xm, Su_xp);
-    x_neighbours<VEC>(Sv_c, hSv, lm.left_edge, lm.right_edge, x0, g.w, Sv_xm, Sv_xp);
-    x_neighbours<VEC>(Sw_c, hSw, lm.left_edge, lm.right_edge, x0, g.w, Sw_xm, Sw_xp);
-    x_neighbours<VEC>(ph_c, hph, lm.left_edge, lm.right_edge, x0, g.w, ph_xm, ph_xp);
-
-    const int zg = g.z0g + z;  // faces are the GLOBAL ones when the level is sharded
-    const float wzp = (zg < g.dg - 1) ? hz2 : 0.f;
-    const float wzm = (zg > 0) ? hz2 : 0.f;
-
-    Vec<VEC> rdu, rdv, rdw;
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      const int x = x0 + i;
-      const float wxp = (x < g.w - 1) ? hx2 : 0.f;
-      const float wxm = (x > 0) ? hx2 : 0.f;
-      const float J11 = __fmul_rn(fx.v[i], fx.v[i]);
-      const float J22 = __fmul_rn(fy.v[i], fy.v[i]);
-      const float J33 = __fmul_rn(fz.v[i], fz.v[i]);
-      const float J12 = __fmul_rn(fx.v[i], fy.v[i]);
-      const float J13 = __fmul_rn(fx.v[i], fz.v[i]);
-      const float J23 = __fmul_rn(fy.v[i], fz.v[i]);
-      const float J14 = __fmul_rn(fx.v[i], ft.v[i]);
-      const float J24 = __fmul_rn(fy.v[i], ft.v[i]);
-      const float J34 = __fmul_rn(fz.v[i], ft.v[i]);
-      const float pc = ph_c.v[i];
-      // face weights: w * (phi_n + phi_c)/2  (solve_3d.cu:462-469); plain products
-      const float axp = __fmul_rn(wxp, __fmul_rn(__fadd_rn(ph_xp.v[i], pc), 0.5f));
-      const float axm = __fmul_rn(wxm, __fmul_rn(__fadd_rn(ph_xm.v[i], pc), 0.5f));
-      const float ayp = __fmul_rn(wyp, __fmul_rn(__fadd_rn(ph_yp.v[i], pc), 0.5f));
-      const float aym = __fmul_rn(wym, __fmul_rn(__fadd_rn(ph_ym.v[i], pc), 0.5f));
-      const float azp = __fmul_rn(wzp, __fmul_rn(__fadd_rn(ph_n.v[i], pc), 0.5f));
-      const float azm = __fmul_rn(wzm, __fmul_rn(__fadd_rn(ph_p.v[i], pc), 0.5f));
-      const float sumH = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(axp, axm), ayp), aym), azp), azm);
-      const float uc = u_c.v[i], vc = v_c.v[i], wc = w_c.v[i];
-      // solve_3d.cu:470-490: seed with the rounded x- product, then one fma per face
-      float sumU = __fmul_rn(axm, __fsub_rn(Su_xm.v[i], uc));
-      sumU = __fmaf_rn(axp, __fsub_rn(Su_xp.v[i], uc), sumU);
-      sumU = __fmaf_rn(ayp, __fsub_rn(Su_yp.v[i], uc), sumU);
-      sumU = __fmaf_rn(aym, __fsub_rn(Su_ym.v[i], uc), sumU);
-      sumU = __fmaf_rn(azp, __fsub_rn(Su_n.v[i], uc), sumU);
-      sumU = __fmaf_rn(azm, __fsub_rn(Su_p.v[i], uc), sumU);
-      float sumV = __fmul_rn(axm, __fsub_rn(Sv_xm.v[i], vc));
-      sumV = __fmaf_rn(axp, __fsub_rn(Sv_xp.v[i], vc), sumV);
-      sumV = __fmaf_rn(ayp, __fsub_rn(Sv_yp.v[i], vc), sumV);
-      sumV = __fmaf_rn(aym, __fsub_rn(Sv_ym.v[i], vc), sumV);
-      sumV = __fmaf_rn(azp, __fsub_rn(Sv_n.v[i], vc), sumV);
-      sumV = __fmaf_rn(azm, __fsub_rn(Sv_p.v[i], vc), sumV);
-      float sumW = __fmul_rn(axm, __fsub_rn(Sw_xm.v[i], wc));
-      sumW = __fmaf_rn(axp, __fsub_rn(Sw_xp.v[i], wc), sumW);
-      sumW = __fmaf_rn(ayp, __fsub_rn(Sw_yp.v[i], wc), sumW);
-      sumW = __fmaf_rn(aym, __fsub_rn(Sw_ym.v[i], wc), sumW);
-      sumW = __fmaf_rn(azp, __fsub_rn(Sw_n.v[i], wc), sumW);
-      sumW = __fmaf_rn(azm, __fsub_rn(Sw_p.v[i], wc), sumW);
-      // solve_3d.cu:492-502
-      const float k = ks.v[i];
-      // numerators as the reference's SASS evaluates them (ptxas contracts the PTX's mul+sub pairs):
-      // n = fma(-J13, dw, fma(-J12, dv, -J14))
-      const float ndu = __fmaf_rn(-J13, dw_c.v[i], __fmaf_rn(-J12, dv_c.v[i], -J14));
-      const float r_du = __fdiv_rn(__fmaf_rn(k, ndu, sumU), __fmaf_rn(J11, k, sumH));
-      const float ndv = __fmaf_rn(-J23, dw_c.v[i], __fmaf_rn(-J12, r_du, -J24));
-      const float r_dv = __fdiv_rn(__fmaf_rn(k, ndv, sumV), __fmaf_rn(J22, k, sumH));
-      const float ndw = __fmaf_rn(-J23, r_dv, __fmaf_rn(-J13, r_du, -J34));
-      const float r_dw = __fdiv_rn(__fmaf_rn(k, ndw, sumW), __fmaf_rn(J33, k, sumH));
-      rdu.v[i] = r_du;
-      rdv.v[i] = r_dv;
-      rdw.v[i] = r_dw;
-    }
-    if (active) {
-      stv<VEC>(a.odu + oc, rdu);
-      stv<VEC>(a.odv + oc, rdv);
-      stv<VEC>(a.odw + oc, rdw);
-    }
-    // ---- rotate ---------------------------------------------------------------------------------
-    Su_p = Su_c; Sv_p = Sv_c; Sw_p = Sw_c; ph_p = ph_c;
-    u_c = u_n; v_c = v_n; w_c = w_n; dv_c = dv_n; dw_c = dw_n;
-    Su_c = Su_n; Sv_c = Sv_n; Sw_c = Sw_n;
-    ph_c = ph_n;
+  // does this warp's tile [tx0, tx1) contain x = 0 or x = w-1 (or run past the volume)?
+  const int tx0 = lm.tile_x * a.lpr * VEC, tx1 = tx0 + a.lpr * VEC;
+  const bool edge = (tx0 == 0) || (tx1 > g.w - 1);  // warp-uniform
+  if constexpr (ROT) {
+    if (edge || !SPEC) sweep_march<VEC, true>(a, g, c, z_begin, z_end);
+    else sweep_march<VEC, false>(a, g, c, z_begin, z_end);
+  } else {
+    if (edge || !SPEC) sweep_march1<VEC, true>(a, g, c, z_begin, z_end);
+    else sweep_march1<VEC, false>(a, g, c, z_begin, z_end);
   }
 }
 
@@ -369,11 +425,11 @@ static int pick_lpr(int w, int vec) {
 }
 
 static void pick_grid(const Dims& g, ZRange zr, int vec, int lpr, int warps_per_block, dim3& grid, dim3& block,
-                      int& zchunk) {
+                      int& zchunk, int wx = 1) {
   const int nz = zr.end - zr.begin;
   block = dim3(32, warps_per_block, 1);
-  const int rows_per_block = warps_per_block * (32 / lpr);
-  const int gx = (g.w + lpr * vec - 1) / (lpr * vec);
+  const int rows_per_block = (warps_per_block / wx) * (32 / lpr);
+  const int gx = (g.w + lpr * vec * wx - 1) / (lpr * vec * wx);
   const int gy = (g.h + rows_per_block - 1) / rows_per_block;
   // enough z chunks for >= ~8 CTAs per SM in flight, but chunks of at least 8 planes (each chunk
   // re-reads two planes of prologue)
@@ -408,28 +464,28 @@ int launch_sweep(const float* fx, const float* fy, const float* fz, const float*
                  float hy, float hz, float alpha, float* odu, float* odv, float* odw, cudaStream_t st) {
   if (zr.end <= zr.begin) return FLOW3D_OK;
   SweepArgs a{fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, odu, odv, odw, g, hx, hy, hz, alpha, 0, 0,
-              zr.begin, zr.end, 32, 0};
+              zr.begin, zr.end, 32, 0, 1};
   const int vec = pick_vec(g);
   static const int pf = env_int("FLOW3D_SWEEP_PF", 2);
   static const int rows = env_int("FLOW3D_SWEEP_ROWS", 4);
   static const int forced_lpr = env_int("FLOW3D_LPR", 0);
   a.pf = pf;
-  static const int pf1 = env_int("FLOW3D_SWEEP_PF1", 0);
-  a.pf1 = pf1;
+  a.pf1 = 0;
   a.lpr = (forced_lpr == 8 || forced_lpr == 16 || forced_lpr == 32) ? forced_lpr : pick_lpr(g.w, vec);
+  static const int wx_env = env_int("FLOW3D_SWEEP_WX", 1);
+  a.wx = (wx_env == 2 || wx_env == 4) && (rows % wx_env == 0) ? wx_env : 1;
   dim3 grid, block;
-  pick_grid(g, zr, vec, a.lpr, rows, grid, block, a.zchunk);
-  static const int unroll = env_int("FLOW3D_SWEEP_UNROLL", 1);
-  static const int minb = env_int("FLOW3D_SWEEP_MINB", 2);
-  (void)unroll;
+  pick_grid(g, zr, vec, a.lpr, rows, grid, block, a.zchunk, a.wx);
+  static const int rot = env_int("FLOW3D_SWEEP_ROT", 0), spec = env_int("FLOW3D_SWEEP_SPEC", 0);
   if (vec == 4) {
-    if (minb == 3) sweep_kernel<4, 1, 3><<<grid, block, 0, st>>>(a);
-    else if (minb == 4) sweep_kernel<4, 1, 4><<<grid, block, 0, st>>>(a);
-    else sweep_kernel<4, 1, 2><<<grid, block, 0, st>>>(a);
+    if (rot && spec) sweep_kernel<4, 2, 1, 1><<<grid, block, 0, st>>>(a);
+    else if (rot) sweep_kernel<4, 2, 1, 0><<<grid, block, 0, st>>>(a);
+    else if (spec) sweep_kernel<4, 2, 0, 1><<<grid, block, 0, st>>>(a);
+    else sweep_kernel<4, 2, 0, 0><<<grid, block, 0, st>>>(a);
   } else if (vec == 2) {
-    sweep_kernel<2, 1, 4><<<grid, block, 0, st>>>(a);
+    sweep_kernel<2, 4, 0, 0><<<grid, block, 0, st>>>(a);
   } else {
-    sweep_kernel<1, 1, 4><<<grid, block, 0, st>>>(a);
+    sweep_kernel<1, 4, 0, 0><<<grid, block, 0, st>>>(a);
   }
   count_launch();
   return check_launch("sweep_kernel");
@@ -467,7 +523,7 @@ __global__ void __launch_bounds__(128) phi_ksi_kernel(const PhiKsiArgs a, int zc
                                                       int lpr) {
   const Dims g = a.g;
   const LaneMap lm = lane_map<VEC>(lpr, g.w, g.h);
-  if ((int)((blockIdx.y * blockDim.y + threadIdx.y) * (32 / lpr)) >= g.h) return;
+  if (lm.first_row >= g.h) return;
   const int y = lm.y;
   const bool active = lm.active;
   const int x0 = lm.x0;

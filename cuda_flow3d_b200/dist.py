@@ -149,6 +149,18 @@ class CabiBackend:
                                        C.byref(sl), f3(h), alpha, *[self._p(t) for t in d_out], self._sp()),
               "sweep_slab")
 
+    def outer_iteration(self, terms, u, v, w, d_cur, d_alt, phi, ksi, h, inner, alpha, eps_s, eps_d, lo1, hi1):
+        """phi/ksi on [lo1,hi1) + `inner` sweeps on shrinking ranges in one C call; returns (cur, alt)"""
+        dims = sz3((u.w, u.t.shape[1], u.dl))
+        sl = self._slab(u, lo1, hi1)
+        flag = C.c_int(0)
+        check(self.L.flow3d_outer_iteration_slab(*[self._p(t) for t in terms], self._p(u.t), self._p(v.t), self._p(w.t),
+                                                 *[self._p(t) for t in d_cur], *[self._p(t) for t in d_alt],
+                                                 self._p(phi), self._p(ksi), dims, u.t.shape[2], C.byref(sl), f3(h),
+                                                 inner, alpha, eps_s, eps_d, C.byref(flag), self._sp()),
+              "outer_iteration_slab")
+        return (d_alt, d_cur) if flag.value else (d_cur, d_alt)
+
     def add3(self, flow, d):
         u = flow[0]
         check(self.L.flow3d_add3(self._p(flow[0].t), self._p(flow[1].t), self._p(flow[2].t), self._p(d[0]),
@@ -239,6 +251,16 @@ class OracleBackend:
                                 *[t.numpy() for t in d_in], phi.numpy(), ksi.numpy(), ww, hh, u.A, u.dg, lo - u.A,
                                 hi - u.A, h[0], h[1], h[2], alpha, *[t.numpy() for t in d_out])
 
+    def outer_iteration(self, terms, u, v, w, d_cur, d_alt, phi, ksi, h, inner, alpha, eps_s, eps_d, lo1, hi1):
+        A, B, d = u.A, u.B, u.dg
+        self.phi_ksi(terms, u, v, w, d_cur[0], d_cur[1], d_cur[2], h, eps_s, eps_d, phi, ksi, lo1, hi1)
+        for j in range(1, inner + 1):
+            lo = lo1 if lo1 == 0 else lo1 + j
+            hi = hi1 if hi1 == d else hi1 - j
+            self.sweep(terms, u, v, w, d_cur, phi, ksi, h, alpha, d_alt, lo, hi)
+            d_cur, d_alt = d_alt, d_cur
+        return d_cur, d_alt
+
     def add3(self, flow, d):
         for c in range(3):
             flow[c].t.add_(d[c])  # one rounded fp32 add per element == add_3d.cu:37-40
@@ -272,7 +294,7 @@ class ShardedFlowSolver:
         self.min_voxels = min_voxels_per_rank
         self.stats = {"sharded_levels": 0, "replicated_levels": 0, "exchanges": 0, "exchange_bytes": 0}
         self.profile = False      # record CUDA events around every batch of sweeps (CabiBackend only)
-        self.sweep_events = []    # (start, end, voxel_sweeps)
+        self.sweep_events = []    # (start, end, voxel_sweeps, phi_ksi_voxels) per outer iteration
 
     # ---- neighbour exchange of ghost planes -------------------------------------------------------
     def _exchange(self, fields, A, B, a, b, H, D):
@@ -365,23 +387,19 @@ class ShardedFlowSolver:
             d_alt = [be.zeros(w, hh, dl) for _ in range(3)]
             phi, ksi = be.zeros(w, hh, dl), be.zeros(w, hh, dl)
             for _ in range(outer):
-                be.phi_ksi(terms, flow[0], flow[1], flow[2], d_cur[0], d_cur[1], d_cur[2], h, P["equation_smoothness"],
-                           P["equation_data"], phi, ksi, lo1, hi1)
                 if prof:
                     e0 = torch.cuda.Event(enable_timing=True)
                     e0.record()
-                    units = 0
-                for j in range(1, inner + 1):
-                    lo = A if A == 0 else A + 1 + j
-                    hi = B if B == d else B - 1 - j
-                    be.sweep(terms, flow[0], flow[1], flow[2], d_cur, phi, ksi, h, P["equation_alpha"], d_alt, lo, hi)
-                    d_cur, d_alt = d_alt, d_cur
-                    if prof:
-                        units += w * hh * (hi - lo)
+                d_cur, d_alt = be.outer_iteration(terms, flow[0], flow[1], flow[2], d_cur, d_alt, phi, ksi, h, inner,
+                                                  P["equation_alpha"], P["equation_smoothness"], P["equation_data"],
+                                                  lo1, hi1)
                 if prof:
                     e1 = torch.cuda.Event(enable_timing=True)
                     e1.record()
-                    self.sweep_events.append((e0, e1, units))
+                    units = 0
+                    for j in range(1, inner + 1):
+                        units += w * hh * ((hi1 if hi1 == d else hi1 - j) - (lo1 if lo1 == 0 else lo1 + j))
+                    self.sweep_events.append((e0, e1, units, w * hh * (hi1 - lo1)))
                 if sharded:
                     self._exchange(d_cur, A, B, a, b, H, d)
             # ---- u += du (:420-438), valid on the whole buffer because the last exchange refreshed du ----
@@ -405,11 +423,13 @@ class ShardedFlowSolver:
         return a, b, [be.to_numpy(f.planes(a, b), dims[0]) for f in flow]
 
     def sweep_profile(self):
-        """(milliseconds, voxel-sweeps) accumulated by the recorded sweep batches; clears the record"""
-        ms = sum(e0.elapsed_time(e1) for e0, e1, _ in self.sweep_events)
-        units = sum(u for _, _, u in self.sweep_events)
+        """(milliseconds, voxel-sweeps, phi/ksi voxel-updates) of the recorded outer iterations (each
+        record brackets one phi/ksi launch + `inner` sweep launches); clears the record"""
+        ms = sum(r[0].elapsed_time(r[1]) for r in self.sweep_events)
+        units = sum(r[2] for r in self.sweep_events)
+        phi_units = sum(r[3] for r in self.sweep_events)
         self.sweep_events = []
-        return ms, units
+        return ms, units, phi_units
 
     def _frame(self, full, full_whd, dims, lo, hi):
         """planes [lo, hi) of a level frame, box-resampled from the replicated full-resolution frame

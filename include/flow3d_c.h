@@ -196,6 +196,17 @@ int flow3d_warp_derivatives_slab(const float* f0, const float* f1, size_t f1_z0_
                                  const float* w, const size_t dims[3], size_t ld,
                                  const flow3d_zslab* slab, const float h[3], float* fx, float* fy,
                                  float* fz, float* ft, void* stream);
+/* One outer iteration on a z-slab in ONE call: phi/ksi on the slab's [z_begin, z_end), then `inner`
+ * Jacobi sweeps on ranges that shrink by one plane per sweep on every side that is NOT a global face
+ * (sweep j computes [z_begin + j, z_end - j) there), ping-ponging between (du,dv,dw) and (tdu,tdv,tdw).
+ * This is the communication-free part of the z-sharded solve (ghost depth inner+1).  On return
+ * *result_in_tmp is 1 when the final iterate is in (tdu,tdv,tdw), 0 when it is in (du,dv,dw). */
+int flow3d_outer_iteration_slab(const float* fx, const float* fy, const float* fz, const float* ft,
+                                const float* u, const float* v, const float* w, float* du, float* dv,
+                                float* dw, float* tdu, float* tdv, float* tdw, float* phi, float* ksi,
+                                const size_t dims[3], size_t ld, const flow3d_zslab* slab,
+                                const float h[3], size_t inner, float alpha, float eps_smooth,
+                                float eps_data, int* result_in_tmp, void* stream);
 int flow3d_median_slab(const float* in, float* out, const size_t dims[3], size_t ld,
                        const flow3d_zslab* slab, size_t radius, void* stream);
 /* resample with the input and the output each given as a slab of its level; x and y passes run on
