@@ -245,29 +245,39 @@ def run_sharded(args, rank, world, local_rank):
     # e2e: every rank uploads both (replicated) frames from pinned host memory and downloads its shard
     e2e = None
     if not args.no_e2e:
-        h0 = torch.empty((D, H, ld), dtype=torch.float32, pin_memory=True)
-        h1 = torch.empty((D, H, ld), dtype=torch.float32, pin_memory=True)
-        h0.copy_(f0)
-        h1.copy_(f1)
-        ho = [torch.empty((b - a, H, ld), dtype=torch.float32, pin_memory=True) for _ in range(3)]
-        step()  # untimed: lets the allocator settle after the pinned allocations
-        barrier()
-        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        x0.record(st)
-        f0.copy_(h0, non_blocking=True)
-        f1.copy_(h1, non_blocking=True)
-        a, b, flow = step()
-        for c in range(3):
-            ho[c].copy_(flow[c], non_blocking=True)
-        x1.record(st)
-        barrier()
-        t = torch.tensor([x0.elapsed_time(x1)], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e_ms = float(t.item())
-        e2e = {"value": (W * H * D) / (e_ms / 1000.0) / 1e6, "unit": "Mvoxel/s",
-               "h2d_bytes_per_step": 2 * D * H * ld * 4, "d2h_bytes_per_step": 3 * (b - a) * H * ld * 4,
-               "ms_per_step": e_ms, "steps": 1, "host_memory": "pinned",
-               "note": "per rank: both full frames up (replicated), own z-shard of the flow down"}
+        ok = torch.ones(1, device=dev)
+        try:
+            h0 = torch.empty((D, H, ld), dtype=torch.float32, pin_memory=True)
+            h1 = torch.empty((D, H, ld), dtype=torch.float32, pin_memory=True)
+            ho = [torch.empty((b - a, H, ld), dtype=torch.float32, pin_memory=True) for _ in range(3)]
+        except Exception:  # not enough lockable host memory on this box
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) > 0:
+            h0.copy_(f0)
+            h1.copy_(f1)
+            step()  # untimed: lets the allocator settle after the pinned allocations
+            barrier()
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x0.record(st)
+            f0.copy_(h0, non_blocking=True)
+            f1.copy_(h1, non_blocking=True)
+            a, b, flow = step()
+            for c in range(3):
+                ho[c].copy_(flow[c], non_blocking=True)
+            x1.record(st)
+            barrier()
+            t = torch.tensor([x0.elapsed_time(x1)], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_ms = float(t.item())
+            e2e = {"value": (W * H * D) / (e_ms / 1000.0) / 1e6, "unit": "Mvoxel/s",
+                   "h2d_bytes_per_step": 2 * D * H * ld * 4, "d2h_bytes_per_step": 3 * (b - a) * H * ld * 4,
+                   "ms_per_step": e_ms, "steps": 1, "host_memory": "pinned",
+                   "note": "per rank: both full frames up (replicated), own z-shard of the flow down"}
+        else:
+            e2e = {"value": None, "unit": "Mvoxel/s", "h2d_bytes_per_step": 2 * D * H * ld * 4,
+                   "d2h_bytes_per_step": 3 * (b - a) * H * ld * 4,
+                   "note": "pinned host allocation failed on this box; end-to-end run skipped"}
     if rank == 0:
         peak, peak_src = hbm_peak()
         achieved = (SWEEP_BYTES * sw_units + PHIKSI_BYTES * phi_units) / (sw_ms / 1000.0) / 1e9 if sw_ms > 0 else 0.0

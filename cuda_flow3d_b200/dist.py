@@ -286,7 +286,7 @@ class ShardedFlowSolver:
     """Coarse-to-fine solve of OpticalFlowE::ComputeFlow (optical_flow_e.cpp:132-601) with every large
     level sharded along z over the ranks of `group`."""
 
-    def __init__(self, backend, rank=None, world=None, min_planes_per_rank=16, min_voxels_per_rank=1 << 21):
+    def __init__(self, backend, rank=None, world=None, min_planes_per_rank=12, min_voxels_per_rank=1 << 18):
         self.be = backend
         self.rank = dist.get_rank() if rank is None else rank
         self.world = dist.get_world_size() if world is None else world
