@@ -203,10 +203,16 @@ def run_sharded(args, rank, world, local_rank):
     dev = be.dev
     st = torch.cuda.current_stream()
     sp = C.c_void_p(st.cuda_stream)
-    f0 = torch.empty((D, H, ld), dtype=torch.float32, device=dev)
-    f1 = torch.empty((D, H, ld), dtype=torch.float32, device=dev)
-    pkg._lib.check(L.flow3d_synth_pair(W, H, D, 0, D, ld, SEED, C.c_void_p(f0.data_ptr()), C.c_void_p(f1.data_ptr()),
-                                       None, None, None, sp), "synth")
+    # every rank holds only the z-slab of the raw frames it needs (own planes + frame ghost + blur halo),
+    # generated on the device
+    from cuda_flow3d_b200.dist import ShardedFrames
+    ghost = 32
+    z_lo, z_hi = ShardedFrames.input_planes(D, rank, world, P["gaussian_sigma"], ghost)
+    nzl = z_hi - z_lo
+    f0 = torch.empty((nzl, H, ld), dtype=torch.float32, device=dev)
+    f1 = torch.empty((nzl, H, ld), dtype=torch.float32, device=dev)
+    pkg._lib.check(L.flow3d_synth_pair(W, H, D, z_lo, nzl, ld, SEED, C.c_void_p(f0.data_ptr()),
+                                       C.c_void_p(f1.data_ptr()), None, None, None, sp), "synth")
     solver = ShardedFlowSolver(be)
 
     def barrier():
@@ -214,7 +220,7 @@ def run_sharded(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     def step():
-        return solver.compute(f0, f1, P, width=W, return_device=True)
+        return solver.compute_slabs(f0, f1, z_lo, (W, H, D), P, return_device=True, frame_ghost=ghost)
 
     for _ in range(args.warmup):
         step()
@@ -247,8 +253,8 @@ def run_sharded(args, rank, world, local_rank):
     if not args.no_e2e:
         ok = torch.ones(1, device=dev)
         try:
-            h0 = torch.empty((D, H, ld), dtype=torch.float32, pin_memory=True)
-            h1 = torch.empty((D, H, ld), dtype=torch.float32, pin_memory=True)
+            h0 = torch.empty((nzl, H, ld), dtype=torch.float32, pin_memory=True)
+            h1 = torch.empty((nzl, H, ld), dtype=torch.float32, pin_memory=True)
             ho = [torch.empty((b - a, H, ld), dtype=torch.float32, pin_memory=True) for _ in range(3)]
         except Exception:  # not enough lockable host memory on this box
             ok.zero_()
@@ -271,11 +277,12 @@ def run_sharded(args, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e_ms = float(t.item())
             e2e = {"value": (W * H * D) / (e_ms / 1000.0) / 1e6, "unit": "Mvoxel/s",
-                   "h2d_bytes_per_step": 2 * D * H * ld * 4, "d2h_bytes_per_step": 3 * (b - a) * H * ld * 4,
+                   "h2d_bytes_per_step": 2 * nzl * H * ld * 4, "d2h_bytes_per_step": 3 * (b - a) * H * ld * 4,
                    "ms_per_step": e_ms, "steps": 1, "host_memory": "pinned",
-                   "note": "per rank: both full frames up (replicated), own z-shard of the flow down"}
+                   "note": "per rank: its z-slab of both raw frames up (own planes + %d ghost + blur halo), own "
+                           "z-shard of the flow down" % ghost}
         else:
-            e2e = {"value": None, "unit": "Mvoxel/s", "h2d_bytes_per_step": 2 * D * H * ld * 4,
+            e2e = {"value": None, "unit": "Mvoxel/s", "h2d_bytes_per_step": 2 * nzl * H * ld * 4,
                    "d2h_bytes_per_step": 3 * (b - a) * H * ld * 4,
                    "note": "pinned host allocation failed on this box; end-to-end run skipped"}
     if rank == 0:
@@ -289,7 +296,9 @@ def run_sharded(args, rank, world, local_rank):
             "config": {"workload": "synthetic %d^3 pair (BASELINE configs[3]) z-sharded over %d GPUs, default "
                                    "parameters (%d levels x 40 outer x 5 inner sweeps, median 5, sigma 2)" % (n, world, nlev),
                        "parallelism": "z-slabs, %d ghost planes, one NCCL send/recv neighbour exchange per outer "
-                                      "iteration; coarse levels replicated" % (P["inner_iterations_count"] + 1),
+                                      "iteration; frames sharded too (coarse level frames assembled by all-gather); "
+                                      "levels too thin to shard are replicated" % (P["inner_iterations_count"] + 1),
+                       "frame_gathers_per_step": stats.get("frame_gathers", 0) / max(1, args.steps),
                        "inputs_larger_than_l2": True, "level_voxels": nsum,
                        "sharded_levels_per_step": stats["sharded_levels"] / max(1, args.steps),
                        "replicated_levels_per_step": stats["replicated_levels"] / max(1, args.steps),

@@ -88,6 +88,7 @@ SIGNATURES = {
                                                   C.c_float, C.c_float, C.c_float, _vp]),
     "flow3d_add3": (C.c_int, [_vp] * 6 + [_sz3, C.c_size_t, _vp]),
     "flow3d_median": (C.c_int, [_vp, _vp, _sz3, C.c_size_t, C.c_size_t, _vp]),
+    "flow3d_gauss_blur_slab": (C.c_int, [_vp, _vp, _vp, _sz3, C.c_size_t, C.POINTER(ZSlab), C.c_float, _vp]),
     "flow3d_sweep_slab": (C.c_int, [_vp] * 12 + [_sz3, C.c_size_t, C.POINTER(ZSlab), _f3, C.c_float] + [_vp] * 4),
     "flow3d_phi_ksi_slab": (C.c_int, [_vp] * 10 + [_sz3, C.c_size_t, C.POINTER(ZSlab), _f3, C.c_float, C.c_float] + [_vp] * 3),
     "flow3d_warp_derivatives_slab": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp, _vp, _vp, _sz3, C.c_size_t,

@@ -126,13 +126,17 @@ static int gauss_taps(float sigma, float* taps, int max_radius) {
   return r;
 }
 
-static int gauss_blur(const float* in, float* out, float* tmp, Dims g, float sigma, cudaStream_t st) {
+// zr: planes whose z pass is computed (x and y passes run on every local plane: the z pass reads
+// `radius` planes around its range)
+static int gauss_blur(const float* in, float* out, float* tmp, Dims g, float sigma, cudaStream_t st,
+                      const ZRange* zr = nullptr) {
   float taps[65];
   const int r = gauss_taps(sigma, taps, 32);
   if (r < 0) return FLOW3D_ERR_UNSUPPORTED;
-  F3D_TRY(launch_conv_axis(in, out, g, taps, r, 0, st));   // rows    (cuda_operation_convolution.cpp:170)
-  F3D_TRY(launch_conv_axis(out, tmp, g, taps, r, 1, st));  // columns (:174)
-  F3D_TRY(launch_conv_axis(tmp, out, g, taps, r, 2, st));  // slices  (:178)
+  const ZRange all{0, g.d};
+  F3D_TRY(launch_conv_axis(in, out, g, taps, r, 0, all, st));   // rows    (cuda_operation_convolution.cpp:170)
+  F3D_TRY(launch_conv_axis(out, tmp, g, taps, r, 1, all, st));  // columns (:174)
+  F3D_TRY(launch_conv_axis(tmp, out, g, taps, r, 2, zr ? *zr : all, st));  // slices  (:178)
   return FLOW3D_OK;
 }
 
@@ -581,6 +585,23 @@ int flow3d_median(const float* in, float* out, const size_t dims[3], size_t ld, 
 }
 
 // ---- z-slab variants -------------------------------------------------------------------------------
+int flow3d_gauss_blur_slab(const float* in, float* out, float* tmp, const size_t dims[3], size_t ld,
+                           const flow3d_zslab* slab, float sigma, void* stream) {
+  F3D_TRY(check_volume(in, dims, ld));
+  F3D_TRY(check_volume(out, dims, ld));
+  F3D_TRY(check_volume(tmp, dims, ld));
+  F3D_TRY(check_slab(dims, slab));
+  if (in == out || !(sigma > 0.f) || !slab) return FLOW3D_ERR_INVALID_ARG;
+  const Dims g = make_slab_dims(dims, ld, slab);
+  const ZRange zr = make_range(g, slab);
+  // every tap of the z pass that lies inside the level must be a plane of the buffer
+  const int r = (int)(size_t)(3 * sigma);
+  if ((g.z0g + zr.begin - r < g.z0g && g.z0g + zr.begin - r >= 0) ||
+      (g.z0g + zr.end - 1 + r >= g.z0g + g.d && g.z0g + zr.end - 1 + r < g.dg))
+    return FLOW3D_ERR_INVALID_ARG;
+  return gauss_blur(in, out, tmp, g, sigma, S(stream), &zr);
+}
+
 int flow3d_sweep_slab(const float* fx, const float* fy, const float* fz, const float* ft,
                       const float* u, const float* v, const float* w, const float* du,
                       const float* dv, const float* dw, const float* phi, const float* ksi,

@@ -19,14 +19,16 @@ struct ConvTaps {
 template <int AXIS>
 __global__ void __launch_bounds__(256) conv_axis_kernel(const float* __restrict__ in,
                                                         float* __restrict__ out, Dims g,
-                                                        ConvTaps taps, int radius) {
+                                                        ConvTaps taps, int radius, int zs) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  const int z = blockIdx.z;
+  const int z = zs + blockIdx.z;
   if (x >= g.w || y >= g.h) return;
   const long long c = (long long)z * g.ps + (long long)y * g.ld + x;
-  const int pos = AXIS == 0 ? x : (AXIS == 1 ? y : z);
-  const int n = AXIS == 0 ? g.w : (AXIS == 1 ? g.h : g.d);
+  // along z the zero padding starts at the GLOBAL faces (z-slabs: every tap inside the level must
+  // be a plane of the buffer -- the caller provides `radius` ghost planes)
+  const int pos = AXIS == 0 ? x : (AXIS == 1 ? y : (g.z0g + z));
+  const int n = AXIS == 0 ? g.w : (AXIS == 1 ? g.h : g.dg);
   const long long stride = AXIS == 0 ? 1 : (AXIS == 1 ? (long long)g.ld : g.ps);
   float sum = 0.f;
   for (int j = -radius; j <= radius; ++j) {
@@ -38,16 +40,17 @@ __global__ void __launch_bounds__(256) conv_axis_kernel(const float* __restrict_
 }
 
 int launch_conv_axis(const float* in, float* out, Dims g, const float* taps_host, int radius,
-                     int axis, cudaStream_t st) {
+                     int axis, ZRange zr, cudaStream_t st) {
   if (radius < 0 || radius > F3D_MAX_BLUR_RADIUS) return FLOW3D_ERR_UNSUPPORTED;
+  if (zr.end <= zr.begin) return FLOW3D_OK;
   ConvTaps t;
   for (int i = 0; i < 2 * radius + 1; ++i) t.t[i] = taps_host[i];
   for (int i = 2 * radius + 1; i < 2 * F3D_MAX_BLUR_RADIUS + 1; ++i) t.t[i] = 0.f;
   dim3 block(32, 8, 1);
-  dim3 grid((g.w + 31) / 32, (g.h + 7) / 8, g.d);
-  if (axis == 0) conv_axis_kernel<0><<<grid, block, 0, st>>>(in, out, g, t, radius);
-  else if (axis == 1) conv_axis_kernel<1><<<grid, block, 0, st>>>(in, out, g, t, radius);
-  else conv_axis_kernel<2><<<grid, block, 0, st>>>(in, out, g, t, radius);
+  dim3 grid((g.w + 31) / 32, (g.h + 7) / 8, zr.end - zr.begin);
+  if (axis == 0) conv_axis_kernel<0><<<grid, block, 0, st>>>(in, out, g, t, radius, zr.begin);
+  else if (axis == 1) conv_axis_kernel<1><<<grid, block, 0, st>>>(in, out, g, t, radius, zr.begin);
+  else conv_axis_kernel<2><<<grid, block, 0, st>>>(in, out, g, t, radius, zr.begin);
   count_launch();
   return check_launch("conv_axis_kernel");
 }

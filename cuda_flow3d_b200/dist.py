@@ -108,6 +108,16 @@ class CabiBackend:
                                        self._sp()), "blur")
         return out
 
+    def blur_slab(self, raw, sigma, lo, hi):
+        """raw: Slab of the full-resolution frame; returns a Slab (same planes) whose planes [lo, hi) hold the
+        blurred frame (zero padding at the global faces only)"""
+        d, h, ld = raw.t.shape
+        out, tmp = torch.empty_like(raw.t), torch.empty_like(raw.t)
+        sl = ZSlab(raw.A, raw.dg, lo - raw.A, hi - raw.A)
+        check(self.L.flow3d_gauss_blur_slab(self._p(raw.t), self._p(out), self._p(tmp), sz3((raw.w, h, d)), ld,
+                                            C.byref(sl), sigma, self._sp()), "gauss_blur_slab")
+        return Slab(out, raw.A, raw.dg, raw.w)
+
     def resample(self, src, src_whd_global, out_whd_global, out_A, out_lo, out_hi, out=None):
         """src: Slab of the input level; returns/fills a Slab of the output level with plane 0 = out_A,
         computing global output planes [out_lo, out_hi)"""
@@ -221,6 +231,20 @@ class OracleBackend:
     def blur(self, full, sigma):
         return torch.from_numpy(self.o.gauss_blur(full.numpy(), sigma))
 
+    def blur_slab(self, raw, sigma, lo, hi):
+        import ctypes as C_
+        a = raw.t.numpy()
+        taps, r = self.o.gauss_taps(sigma)
+        t1 = self.o.conv_axis(a, taps, r, 0)
+        t2 = self.o.conv_axis(t1, taps, r, 1)
+        out = np.zeros_like(a)
+        f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+        fn = self.o.lib.o_conv_z_slab
+        fn.argtypes = [f32p, f32p, C_.c_size_t, C_.c_size_t, C_.c_long, C_.c_long, C_.c_long, C_.c_long, f32p, C_.c_int]
+        d, hh, ww = a.shape
+        fn(t2, out, ww, hh, raw.A, raw.dg, lo - raw.A, hi - raw.A, np.ascontiguousarray(taps, np.float32), r)
+        return Slab(torch.from_numpy(out), raw.A, raw.dg, raw.w)
+
     def resample(self, src, src_whd_global, out_whd_global, out_A, out_lo, out_hi, out=None):
         iw, ih, idg = src_whd_global
         ow, oh, odg = out_whd_global
@@ -279,6 +303,111 @@ class OracleBackend:
 
     def to_numpy(self, t, w):
         return t[:, :, :w].contiguous().numpy()
+
+
+# =====================================================================================================
+class ReplicatedFrames:
+    """both blurred full-resolution frames live on every rank"""
+    global_reach = False
+
+    def __init__(self, solver, F0, F1, whd):
+        self.s, self.whd = solver, whd
+        W, Hh, D = whd
+        self.full = [Slab(F0, 0, D, W), Slab(F1, 0, D, W)]
+
+    def level_frame(self, which, level, dims, lo, hi):
+        if level == 0:
+            return Slab(self.full[which].planes(lo, hi), lo, dims[2], dims[0])
+        return self.s._frame(self.full[which], self.whd, dims, lo, hi)
+
+
+class ShardedFrames:
+    """each rank holds only a z-slab [Va, Vb) of the blurred full-resolution frames (its own planes plus
+    `ghost` planes per side).  A level frame is resampled locally when every rank's request fits its
+    slab; otherwise (coarse levels, whose source intervals are long) every rank resamples the planes whose
+    source interval starts in its own range and the level frame is assembled with one all-gather."""
+    global_reach = True
+
+    def __init__(self, solver, raw0, raw1, raw_z0, whd, sigma, ghost):
+        self.s, self.whd, self.ghost = solver, whd, ghost
+        be = solver.be
+        W, Hh, D = whd
+        fa, fb = own_range(D, solver.rank, solver.world)
+        self.Va, self.Vb = max(0, fa - ghost), min(D, fb + ghost)
+        self.slabs = []
+        for raw in (raw0, raw1):
+            rs = Slab(raw, raw_z0, D, W)
+            if sigma > 0:
+                r = int(3 * sigma)
+                assert rs.A <= max(0, self.Va - r) and rs.B >= min(D, self.Vb + r), "raw slab lacks blur halo planes"
+                bl = be.blur_slab(rs, sigma, self.Va, self.Vb)
+            else:
+                bl = rs
+            self.slabs.append(Slab(bl.planes(self.Va, self.Vb), self.Va, D, W))
+        self._gathered = {}
+
+    @staticmethod
+    def input_planes(D, rank, world, sigma, ghost):
+        """planes [lo, hi) of the raw frames a rank has to be given"""
+        fa, fb = own_range(D, rank, world)
+        r = int(3 * sigma) if sigma > 0 else 0
+        return max(0, fa - ghost - r), min(D, fb + ghost + r)
+
+    def _fits_everywhere(self, dims, ranges):
+        """ranges[r] = (lo, hi) requested by rank r; True if every request's source interval lies in that
+        rank's blurred slab (same answer on every rank)"""
+        D = self.whd[2]
+        for r, (lo, hi) in enumerate(ranges):
+            fa, fb = own_range(D, r, self.s.world)
+            Va, Vb = max(0, fa - self.ghost), min(D, fb + self.ghost)
+            s_lo, s_hi = source_range(lo, hi, D, dims[2]) if dims[2] != D else (lo, hi)
+            if s_lo < Va or s_hi > Vb:
+                return False
+        return True
+
+    def level_frame(self, which, level, dims, lo, hi, all_ranges=None):
+        be = self.s.be
+        w, hh, d = dims
+        D = self.whd[2]
+        if all_ranges is not None and self._fits_everywhere(dims, all_ranges):
+            if level == 0:
+                return Slab(self.slabs[which].planes(lo, hi), lo, d, w)
+            return self.s._frame(self.slabs[which], self.whd, dims, lo, hi)
+        assert level != 0, "frame ghost depth too small for the finest level (raise frame_ghost)"
+        key = (which, level)
+        if key not in self._gathered:
+            self._gathered = {k: v for k, v in self._gathered.items() if k[1] == level}  # drop older levels
+            self._gathered[key] = self._gather(which, dims)
+        full = self._gathered[key]
+        return Slab(full.planes(lo, hi), lo, d, w)
+
+    def _gather(self, which, dims):
+        be = self.s.be
+        w, hh, d = dims
+        W, Hh, D = self.whd
+        world = self.s.world
+        # output plane o belongs to the rank in whose own full-resolution range its source interval starts
+        delta = f32(D) / f32(d)
+        starts = np.floor(np.arange(d, dtype=np.float32) * delta).astype(np.int64)
+        bounds = [int(np.searchsorted(starts, own_range(D, r, world)[0], side="left")) for r in range(world)] + [d]
+        p_lo, p_hi = bounds[self.s.rank], bounds[self.s.rank + 1]
+        n_max = max(bounds[r + 1] - bounds[r] for r in range(world))
+        piece = be.zeros(w, hh, max(n_max, 1))
+        if p_hi > p_lo:
+            s_lo, s_hi = source_range(p_lo, p_hi, D, d)
+            assert self.Va <= s_lo and s_hi <= self.Vb, "frame ghost depth smaller than one coarse source interval"
+            src = Slab(self.slabs[which].planes(s_lo, s_hi), s_lo, D, W)
+            out = Slab(piece[:p_hi - p_lo], p_lo, d, w)
+            be.resample(src, self.whd, dims, p_lo, p_lo, p_hi, out=out)
+        pieces = [torch.empty_like(piece) for _ in range(world)]
+        dist.all_gather(pieces, piece)
+        full = be.empty(w, hh, d)
+        for r in range(world):
+            n = bounds[r + 1] - bounds[r]
+            if n > 0:
+                full[bounds[r]:bounds[r + 1]] = pieces[r][:n]
+        self.s.stats["frame_gathers"] = self.s.stats.get("frame_gathers", 0) + 1
+        return Slab(full, 0, d, w)
 
 
 # =====================================================================================================
@@ -347,8 +476,31 @@ class ShardedFlowSolver:
         prof = self.profile
         if P["gaussian_sigma"] > 0:
             F0, F1 = be.blur(F0, P["gaussian_sigma"]), be.blur(F1, P["gaussian_sigma"])
-        fullF0 = Slab(F0, 0, D, W)
-        fullF1 = Slab(F1, 0, D, W)
+        frames = ReplicatedFrames(self, F0, F1, (W, Hh, D))
+        return self._solve(frames, (W, Hh, D), sched, P, level_cb, return_device)
+
+    def compute_slabs(self, raw0, raw1, raw_z0, whd, params=None, level_cb=None, return_device=False,
+                      frame_ghost=32):
+        """Like compute(), but every rank passes only a z-slab of the two RAW frames (backend tensors
+        (dl,H,ld) or numpy (dl,H,W)) starting at global plane raw_z0 and covering at least
+        ShardedFrames.input_planes(...): nothing full-size is ever held by one rank (2048^3 and up)."""
+        be = self.be
+        P = dict(DEFAULTS)
+        P.update(params or {})
+        W, Hh, D = whd
+        if isinstance(raw0, np.ndarray):
+            raw0, raw1 = be.from_numpy_full(raw0), be.from_numpy_full(raw1)
+        be.w_full = W
+        sched = self._schedule(W, Hh, D, P)
+        frames = ShardedFrames(self, raw0, raw1, raw_z0, (W, Hh, D), P["gaussian_sigma"], frame_ghost)
+        return self._solve(frames, (W, Hh, D), sched, P, level_cb, return_device)
+
+    def _solve(self, frames, whd, sched, P, level_cb, return_device):
+        be = self.be
+        W, Hh, D = whd
+        inner, outer = int(P["inner_iterations_count"]), int(P["outer_iterations_count"])
+        H = inner + 1
+        prof = self.profile
         prev = None  # (dims, [u,v,w] Slabs, valid_lo, valid_hi)
         for (level, dims, h) in sched:
             w, hh, d = dims
@@ -370,14 +522,25 @@ class ShardedFlowSolver:
                 self._exchange([f.t for f in flow], A, B, a, b, H, d)
             # ---- frames of this level, resampled from the replicated full-resolution frames -------------
             hz = h[2]
-            reach = int(math.ceil(be.absmax(flow[2]) / float(hz))) + 2 if prev is not None else 1
+            wmax = be.absmax(flow[2]) if prev is not None else 0.0
+            if frames.global_reach and self.world > 1:  # same reach on every rank => same local/gather decision
+                t = torch.tensor([wmax], dtype=torch.float32, device=be.dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                wmax = float(t.item())
+            reach = int(math.ceil(wmax / float(hz))) + 2 if prev is not None else 1
             A1, B1 = max(0, A - reach), min(d, B + reach)
-            if level == 0:
-                f0l = Slab(fullF0.planes(A, B), A, d, w)
-                f1l = Slab(fullF1.planes(A1, B1), A1, d, w)
+            if frames.global_reach:
+                rng0, rng1 = [], []
+                for r in range(self.world):
+                    ra, rb = own_range(d, r, self.world) if sharded else (0, d)
+                    rA, rB = (max(0, ra - H), min(d, rb + H)) if sharded else (0, d)
+                    rng0.append((rA, rB))
+                    rng1.append((max(0, rA - reach), min(d, rB + reach)))
+                f0l = frames.level_frame(0, level, dims, A, B, rng0)
+                f1l = frames.level_frame(1, level, dims, A1, B1, rng1)
             else:
-                f0l = self._frame(fullF0, (W, Hh, D), dims, A, B)
-                f1l = self._frame(fullF1, (W, Hh, D), dims, A1, B1)
+                f0l = frames.level_frame(0, level, dims, A, B)
+                f1l = frames.level_frame(1, level, dims, A1, B1)
             # ---- warp + derivatives on every plane the solver touches ----------------------------------
             lo1 = A if A == 0 else A + 1
             hi1 = B if B == d else B - 1

@@ -179,6 +179,11 @@ int flow3d_median(const float* in, float* out, const size_t dims[3], size_t ld, 
                   void* stream);
 
 /* ---- z-slab (multi-GPU) variants: identical arithmetic, boundary handling per flow3d_zslab ------ */
+/* pre-blur of a z-slab of the full-resolution frame: zero padding at the global faces only; the
+ * slab must hold (size_t)(3*sigma) ghost planes around [z_begin, z_end) (or reach a global face);
+ * planes outside the range receive the x/y-blurred intermediate and must not be used */
+int flow3d_gauss_blur_slab(const float* in, float* out, float* tmp, const size_t dims[3], size_t ld,
+                           const flow3d_zslab* slab, float sigma, void* stream);
 int flow3d_sweep_slab(const float* fx, const float* fy, const float* fz, const float* ft,
                       const float* u, const float* v, const float* w, const float* du,
                       const float* dv, const float* dw, const float* phi, const float* ksi,

@@ -140,6 +140,24 @@ void o_conv_axis(const float* in, float* out, size_t w, size_t h, size_t d, cons
       }
 }
 
+// z pass on a slab: local plane 0 = global z0g of a volume of global depth dg; zero padding at the
+// global faces only; computes local planes [zs, ze)
+void o_conv_z_slab(const float* in, float* out, size_t w, size_t h, long z0g, long dg, long zs, long ze,
+                   const float* taps, int radius) {
+#pragma omp parallel for schedule(static)
+  for (long z = zs; z < ze; ++z)
+    for (long y = 0; y < (long)h; ++y)
+      for (long x = 0; x < (long)w; ++x) {
+        float sum = 0;
+        for (int j = -radius; j <= radius; j++) {
+          const long zg = z0g + z + j;
+          float v = (zg >= 0 && zg < dg) ? in[IDX(x, y, z + j, w, h)] : 0.f;
+          sum = std::fmaf(taps[radius - j], v, sum);
+        }
+        out[IDX(x, y, z, w, h)] = sum;
+      }
+}
+
 // cuda_operation_convolution.cpp:159-180: rows(in->out), columns(out->tmp), slices(tmp->out)
 void o_gauss_blur(const float* in, float* out, float* tmp, size_t w, size_t h, size_t d,
                   float sigma) {

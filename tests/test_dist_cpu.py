@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, shape, params, out_dir):
+def _worker(rank, world, port, shape, params, out_dir, slabs=False):
     import sys
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -35,21 +35,31 @@ def _worker(rank, world, port, shape, params, out_dir):
     f0 = smooth_volume(shape, 21)
     f1 = np.ascontiguousarray(np.roll(f0, (1, -1, 2), axis=(0, 1, 2)))
     solver = ShardedFlowSolver(OracleBackend(o), min_planes_per_rank=8, min_voxels_per_rank=1)
-    a, b, flow = solver.compute(f0, f1, params)
+    if slabs:
+        # every rank is given only the planes of the raw frames it needs (sharded frames)
+        from cuda_flow3d_b200.dist import ShardedFrames
+        ghost = 12
+        lo, hi = ShardedFrames.input_planes(shape[0], rank, world, params.get("gaussian_sigma", 2.0), ghost)
+        a, b, flow = solver.compute_slabs(np.ascontiguousarray(f0[lo:hi]), np.ascontiguousarray(f1[lo:hi]), lo,
+                                          (shape[2], shape[1], shape[0]), params, frame_ghost=ghost)
+    else:
+        a, b, flow = solver.compute(f0, f1, params)
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), a=a, b=b, u=flow[0], v=flow[1], w=flow[2],
-             sharded=solver.stats["sharded_levels"], exchanges=solver.stats["exchanges"])
+             sharded=solver.stats["sharded_levels"], exchanges=solver.stats["exchanges"],
+             gathers=solver.stats.get("frame_gathers", 0))
     dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("shape,params", [
-    ((40, 18, 22), dict(outer_iterations_count=2, inner_iterations_count=3, warp_levels_count=12, median_radius=5)),
+    ((48, 18, 22), dict(outer_iterations_count=2, inner_iterations_count=3, warp_levels_count=12, median_radius=5)),
     ((36, 16, 20), dict(outer_iterations_count=2, inner_iterations_count=2, warp_levels_count=6, median_radius=3,
                         gaussian_sigma=0.0)),
 ])
-def test_two_rank_sharded_solve_equals_single_process(oracle, tmp_path, shape, params):
+@pytest.mark.parametrize("slabs", [False, True])
+def test_two_rank_sharded_solve_equals_single_process(oracle, tmp_path, shape, params, slabs):
     world = 2
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, shape, params, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, shape, params, str(tmp_path), slabs), nprocs=world, join=True)
     f0 = smooth_volume(shape, 21)
     f1 = np.ascontiguousarray(np.roll(f0, (1, -1, 2), axis=(0, 1, 2)))
     ref = oracle.compute_flow(f0, f1, params)
@@ -59,6 +69,8 @@ def test_two_rank_sharded_solve_equals_single_process(oracle, tmp_path, shape, p
         a, b = int(z["a"]), int(z["b"])
         assert int(z["sharded"]) >= 2, "the test must exercise sharded levels"
         assert int(z["exchanges"]) > 0
+        if slabs and params["warp_levels_count"] >= 12:
+            assert int(z["gathers"]) > 0, "coarse levels must have used the all-gather path"
         for c, name in enumerate("uvw"):
             assert np.array_equal(z[name], ref[c][a:b]), "rank %d flow_%s planes [%d,%d) differ" % (r, name, a, b)
         covered += b - a

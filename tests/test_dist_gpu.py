@@ -19,7 +19,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, shape, params, out_dir):
+def _worker(rank, world, port, shape, params, out_dir, slabs):
     import sys
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -33,13 +33,21 @@ def _worker(rank, world, port, shape, params, out_dir):
     f0 = smooth_volume(shape, 21)
     f1 = np.ascontiguousarray(np.roll(f0, (1, -1, 2), axis=(0, 1, 2)))
     solver = ShardedFlowSolver(CabiBackend(rank), min_planes_per_rank=8, min_voxels_per_rank=1)
-    a, b, flow = solver.compute(f0, f1, params)
+    if slabs:
+        from cuda_flow3d_b200.dist import ShardedFrames
+        ghost = 16
+        lo, hi = ShardedFrames.input_planes(shape[0], rank, world, 2.0, ghost)
+        a, b, flow = solver.compute_slabs(np.ascontiguousarray(f0[lo:hi]), np.ascontiguousarray(f1[lo:hi]), lo,
+                                          (shape[2], shape[1], shape[0]), params, frame_ghost=ghost)
+    else:
+        a, b, flow = solver.compute(f0, f1, params)
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), a=a, b=b, u=flow[0], v=flow[1], w=flow[2],
-             sharded=solver.stats["sharded_levels"])
+             sharded=solver.stats["sharded_levels"], gathers=solver.stats.get("frame_gathers", 0))
     dist.destroy_process_group()
 
 
-def test_sharded_equals_single_gpu(gpu, tmp_path):
+@pytest.mark.parametrize("slabs", [False, True])
+def test_sharded_equals_single_gpu(gpu, tmp_path, slabs):
     import torch
     import torch.multiprocessing as mp
     world = min(torch.cuda.device_count(), 4)
@@ -47,7 +55,7 @@ def test_sharded_equals_single_gpu(gpu, tmp_path):
         pytest.skip("needs >= 2 GPUs")
     shape = (96, 40, 72)
     params = dict(outer_iterations_count=3, inner_iterations_count=5, warp_levels_count=14)
-    mp.spawn(_worker, args=(world, _free_port(), shape, params, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), shape, params, str(tmp_path), slabs), nprocs=world, join=True)
     f0 = smooth_volume(shape, 21)
     f1 = np.ascontiguousarray(np.roll(f0, (1, -1, 2), axis=(0, 1, 2)))
     d, h, w = shape
