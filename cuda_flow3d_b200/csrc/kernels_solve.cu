@@ -412,6 +412,11 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const SweepArgs a) {
   }
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+
 // lanes per row segment: the power of two in {32,16,8} that wastes the fewest lanes for this width
 static int pick_lpr(int w, int vec) {
   int best = 32;
@@ -438,23 +443,20 @@ static void pick_grid(const Dims& g, ZRange zr, int vec, int lpr, int warps_per_
   long long nchunks = (want + per_plane - 1) / per_plane;
   if (nchunks < 1) nchunks = 1;
   long long len = (nz + nchunks - 1) / nchunks;
-  if (len < 8) len = 8;
+  static const int min_chunk = env_int("FLOW3D_MIN_ZCHUNK", 8);
+  if (len < min_chunk) len = min_chunk;
   if (len > nz) len = nz;
   if (len < 1) len = 1;
   zchunk = (int)len;
   grid = dim3(gx, gy, (nz + zchunk - 1) / zchunk);
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return (e && *e) ? atoi(e) : dflt;
-}
 
 static int pick_vec(const Dims& g) {
   static const int forced = env_int("FLOW3D_SWEEP_VEC", 0);  // tuning knob (results are identical)
   if (forced == 1 || forced == 2 || forced == 4) return forced;
-  if (g.w >= 96) return 4;
-  if (g.w >= 48) return 2;
+  if (g.w >= 224) return 4;  // measured on B200: VEC=2 (more warps) wins below ~200 columns
+  if (g.w >= 32) return 2;
   return 1;
 }
 
