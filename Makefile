@@ -10,7 +10,8 @@ PKG       := cuda_flow3d_b200
 CSRC      := $(PKG)/csrc
 LIB       := $(PKG)/libflow3d_b200.so
 CU_SRCS   := $(CSRC)/flow3d_cabi.cu $(CSRC)/kernels_solve.cu $(CSRC)/kernels_pyramid.cu \
-             $(CSRC)/kernels_warp.cu $(CSRC)/kernels_median.cu $(CSRC)/kernels_synth.cu
+             $(CSRC)/kernels_warp.cu $(CSRC)/kernels_median.cu $(CSRC)/kernels_synth.cu \
+             $(CSRC)/kernels_diag.cu
 CU_OBJS   := $(CU_SRCS:.cu=.o)
 HOST_SRCS := $(wildcard $(PKG)/host/*.cpp)
 HOST_OBJS := $(HOST_SRCS:.cpp=.o)

@@ -3,6 +3,7 @@
 //
 //   flow3d_cli --dims W H D --frame0 a.raw --frame1 b.raw [--f32] [--out prefix] [--vtk file.vtk]
 //              [--param key=value ...] [--reps N] [--device k] [--verbose]
+//              [--diagnostics] [--tolerance T] [--warped PREFIX]
 //   flow3d_cli --pairs "frames_%04d.raw" FIRST LAST ...   consecutive frame pairs, solver kept alive
 #include <chrono>
 #include <cstdio>
@@ -21,7 +22,11 @@ void usage(const char* a0) {
   std::printf(
       "usage: %s --dims W H D --frame0 F0 --frame1 F1 [--f32] [--out PREFIX] [--vtk FILE]\n"
       "          [--param key=value]... [--reps N] [--device K] [--verbose]\n"
+      "          [--diagnostics] [--tolerance T] [--warped PREFIX]\n"
       "       %s --dims W H D --pairs PATTERN FIRST LAST [--f32] [--out PREFIX] ...\n"
+      "--diagnostics prints the Jacobi update norm per level; --tolerance T stops a level once the RMS\n"
+      "update falls below T voxels (not the reference's fixed iteration count); --warped writes the\n"
+      "registered frame 1 (PREFIX_warped.raw) and |warped - frame0| (PREFIX_error.raw), float32.\n"
       "inputs are headerless RAW volumes, x fastest: uint8 by default, float32 with --f32.\n"
       "parameters: warp_levels_count warp_scale_factor outer_iterations_count inner_iterations_count\n"
       "            equation_alpha equation_smoothness equation_data median_radius gaussian_sigma\n",
@@ -50,7 +55,9 @@ bool read_frame(Data3D& d, const std::string& path, bool f32, size_t W, size_t H
 
 int main(int argc, char** argv) {
   size_t W = 0, H = 0, D = 0;
-  std::string f0, f1, out, vtk, pattern;
+  std::string f0, f1, out, vtk, pattern, warped_prefix;
+  bool diagnostics = false;
+  float tolerance = 0.f;
   long first = 0, last = -1;
   bool f32 = false, verbose = false;
   int reps = 1, device = 0;
@@ -66,6 +73,9 @@ int main(int argc, char** argv) {
     else if (a == "--out" && need(1)) out = argv[++i];
     else if (a == "--vtk" && need(1)) vtk = argv[++i];
     else if (a == "--f32") f32 = true;
+    else if (a == "--diagnostics") diagnostics = true;
+    else if (a == "--tolerance" && need(1)) { tolerance = std::strtof(argv[++i], nullptr); diagnostics = true; }
+    else if (a == "--warped" && need(1)) warped_prefix = argv[++i];
     else if (a == "--verbose") verbose = true;
     else if (a == "--reps" && need(1)) reps = std::atoi(argv[++i]);
     else if (a == "--device" && need(1)) device = std::atoi(argv[++i]);
@@ -92,6 +102,7 @@ int main(int argc, char** argv) {
   solver.silent = !verbose;
   DataSize4 size = {W, H, D, 0};
   if (!solver.Initialize(size)) return 1;
+  if (diagnostics && !solver.SetDiagnostics(true, tolerance)) return 1;
   Data3D u(W, H, D), v(W, H, D), w(W, H, D);
   Data3D a, b;
 
@@ -114,6 +125,14 @@ int main(int argc, char** argv) {
         return 3;
     }
     if (!vtk.empty() && !Data3D::WriteFlowToFileVTK(vtk.c_str(), u, v, w)) return 3;
+    if (diagnostics) solver.PrintDiagnostics();
+    if (!warped_prefix.empty()) {
+      Data3D warped(W, H, D), err(W, H, D);
+      if (!solver.WarpFrame(a, b, u, v, w, warped, &err)) return 1;
+      const std::string tag = prefix.empty() ? warped_prefix : warped_prefix + prefix.substr(out.size());
+      if (!warped.WriteRAWToFileF32((tag + "_warped.raw").c_str()) || !err.WriteRAWToFileF32((tag + "_error.raw").c_str()))
+        return 3;
+    }
     return 0;
   };
 

@@ -227,6 +227,7 @@ def run_sharded(args, rank, world, local_rank):
     barrier()
     solver.profile = True
     solver.sweep_events = []
+    solver.phase_marks = []
     for k in solver.stats:
         solver.stats[k] = 0
     L.flow3d_reset_launch_count()
@@ -245,6 +246,7 @@ def run_sharded(args, rank, world, local_rank):
     ms_per_step = float(t.item()) / args.steps
     value = (W * H * D) / (ms_per_step / 1000.0) / 1e6
     sw_ms, sw_units, phi_units = solver.sweep_profile()
+    phases = {k: v / args.steps for k, v in solver.phase_profile().items()}
     solver.profile = False
     stats = dict(solver.stats)
 
@@ -312,6 +314,7 @@ def run_sharded(args, rank, world, local_rank):
                          "algorithmic_bytes_per_phi_ksi_voxel": PHIKSI_BYTES,
                          "voxel_sweeps": sw_units, "phi_ksi_voxels": phi_units, "traffic": None},
         }
+        line["phase_ms_per_step_rank0"] = phases
         if e2e:
             line["e2e"] = e2e
         print(json.dumps(line))
@@ -436,6 +439,32 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
         e2e["host_equals_device_result"] = bool(torch.equal(chk, ho[0]))
 
+    # ---- accuracy: endpoint error of the computed flow against the analytic ground truth ------------
+    epe = None
+    if rank == 0:
+        try:
+            tr = [torch.empty(vol, dtype=torch.float32, device=dev) for _ in range(3)]
+            pkg._lib.check(L.flow3d_synth_pair(W, H, D, 0, D, ld, SEED + rank, None, None,
+                                               C.c_void_p(tr[0].data_ptr()), C.c_void_p(tr[1].data_ptr()),
+                                               C.c_void_p(tr[2].data_ptr()), sp), "synth truth")
+            sq = None
+            mag = None
+            for o, t in zip(outs, tr):
+                dlt = (o.view(D, H, ld)[:, :, :W] - t.view(D, H, ld)[:, :, :W]).double()
+                sq = dlt * dlt if sq is None else sq + dlt * dlt
+                tt = t.view(D, H, ld)[:, :, :W].double()
+                mag = tt * tt if mag is None else mag + tt * tt
+                del dlt, tt
+            e = sq.sqrt()
+            m = 16
+            epe = {"mean": float(e.mean().item()), "interior_mean": float(e[m:-m, m:-m, m:-m].mean().item()),
+                   "interior_median": float(e[m:-m, m:-m, m:-m].flatten()[::37].median().item()),
+                   "truth_mean_magnitude": float(mag.sqrt().mean().item()), "unit": "voxel",
+                   "note": "flow vs the analytic rigid motion (f1(x+flow)=f0(x)); interior = 16-voxel margin removed"}
+            del tr, sq, mag, e
+        except Exception as ex:
+            epe = {"error": repr(ex)}
+
     if rank == 0:
         peak, peak_src = hbm_peak()
         sweep_s = stage_ms[4] / 1000.0
@@ -466,6 +495,8 @@ def run_ours(args, rank, world, local_rank):
         }
         if e2e:
             line["e2e"] = e2e
+        if epe:
+            line["endpoint_error"] = epe
         if world == 1 and not args.no_cpu_baseline:
             solver_passes = nsum * (P["outer_iterations_count"] * (1 + P["inner_iterations_count"]))
             try:

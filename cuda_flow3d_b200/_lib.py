@@ -109,6 +109,11 @@ SIGNATURES = {
     "flow3d_solver_set_profiling": (C.c_int, [_vp, C.c_int]),
     "flow3d_solver_stage_times": (C.c_int, [_vp, C.c_float * 8, C.c_double * 8, C.c_uint64 * 8]),
     "flow3d_solver_set_level_callback": (C.c_int, [_vp, LEVEL_CALLBACK, _vp]),
+    "flow3d_update_norm_workspace_bytes": (C.c_size_t, []),
+    "flow3d_update_norm": (C.c_int, [_vp] * 6 + [_sz3, C.c_size_t, C.POINTER(ZSlab), _vp, _vp, _vp]),
+    "flow3d_solver_set_diagnostics": (C.c_int, [_vp, C.c_int, C.c_float]),
+    "flow3d_solver_diagnostics": (C.c_int, [_vp, C.POINTER(C.c_size_t), _vp, _vp, _vp, C.c_size_t,
+                                            C.POINTER(C.c_size_t)]),
     "flow3d_synth_pair": (C.c_int, [C.c_size_t] * 6 + [C.c_uint64] + [_vp] * 6),
 }
 

@@ -270,6 +270,21 @@ class _Ops:
         check(L.flow3d_median(x.ptr, out.ptr, sz3(x.dims), x.ld, int(radius), None), "flow3d_median")
         return out.numpy()
 
+    def update_norm(self, a, b, z_range=None):
+        """(sum |a-b|^2, max |a-b|) over three component pairs (flow3d_update_norm)"""
+        L = load()
+        d = self._dv(*a, *b)
+        out = DeviceVolume((4, 1, 1))
+        ws = C.c_void_p()
+        check(L.flow3d_malloc(C.byref(ws), L.flow3d_update_norm_workspace_bytes()), "malloc")
+        sl = None
+        if z_range is not None:
+            sl = C.byref(_lib.ZSlab(0, d[0].dims[2], int(z_range[0]), int(z_range[1])))
+        check(L.flow3d_update_norm(*[t.ptr for t in d], sz3(d[0].dims), d[0].ld, sl, out.ptr, ws, None), "update_norm")
+        raw = out.numpy().reshape(-1).view(np.float64)
+        L.flow3d_free(ws)
+        return float(raw[0]), float(raw[1])
+
     def synth_pair(self, W, H, D, seed=20240521, truth=True):
         L = load()
         f0, f1 = DeviceVolume((W, H, D)), DeviceVolume((W, H, D))
@@ -373,6 +388,29 @@ class OpticalFlowE:
             ms = (C.c_float * 2)()
             L.flow3d_solver_last_timing(self._solver, ms)
             print("Total GPU computation time: % 4.4fs" % (ms[0] / 1000.0))  # optical_flow_e.cpp:585
+
+    def set_diagnostics(self, enable=True, update_tolerance=0.0):
+        """Record the Jacobi update norm per level and outer iteration (flow3d_solver_set_diagnostics).
+        update_tolerance > 0 stops a level early once the RMS update drops below it (non-parity mode)."""
+        check(load().flow3d_solver_set_diagnostics(self._solver, 1 if enable else 0, float(update_tolerance)),
+              "set_diagnostics")
+
+    def diagnostics(self):
+        """[(outer iterations run, rms[...], max_abs[...])] per level, coarsest first"""
+        L = load()
+        nl, nr = C.c_size_t(0), C.c_size_t(0)
+        check(L.flow3d_solver_diagnostics(self._solver, C.byref(nl), None, None, None, 0, C.byref(nr)), "diagnostics")
+        cap = max(int(nl.value), int(nr.value), 1)
+        per = (C.c_size_t * cap)()
+        rms = (C.c_double * cap)()
+        mx = (C.c_double * cap)()
+        check(L.flow3d_solver_diagnostics(self._solver, C.byref(nl), per, rms, mx, cap, C.byref(nr)), "diagnostics")
+        out, k = [], 0
+        for l in range(int(nl.value)):
+            n = int(per[l])
+            out.append((n, [rms[k + i] for i in range(n)], [mx[k + i] for i in range(n)]))
+            k += n
+        return out
 
     def last_timing_ms(self):
         ms = (C.c_float * 2)()

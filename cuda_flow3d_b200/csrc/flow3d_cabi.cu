@@ -160,11 +160,25 @@ static int resample(const float* in, const size_t id[3], size_t in_ld, float* ou
   return FLOW3D_OK;
 }
 
+// Opt-in convergence diagnostics (kernels_diag.cu): one {sum |update|^2, max |update|} record per
+// outer iteration, measured between the last two Jacobi iterates.  With tol > 0 the level stops as
+// soon as the RMS update falls below tol (NOT the reference's behaviour: it always runs `outer`
+// iterations; results then differ from the parity path).
+struct Diag {
+  double* dev = nullptr;    // 2 doubles per record
+  double* host = nullptr;   // pinned mirror, same layout
+  void* workspace = nullptr;
+  size_t capacity = 0;      // records
+  size_t used = 0;
+  float tol = 0.f;
+};
+
 static int solve_level(const float* fx, const float* fy, const float* fz, const float* ft,
                        const float* u, const float* v, const float* w, float* du, float* dv,
                        float* dw, float* phi, float* ksi, float* tdu, float* tdv, float* tdw, Dims g,
                        const float h[3], size_t outer, size_t inner, float alpha, float eps_s,
-                       float eps_d, cudaStream_t st, StageTimer* tm = nullptr) {
+                       float eps_d, cudaStream_t st, StageTimer* tm = nullptr, Diag* dg = nullptr,
+                       size_t* outer_done = nullptr) {
   const size_t bytes = (size_t)g.ps * g.d * sizeof(float);
   const double nvox = (double)g.w * g.h * g.d;
   if (tm) tm->mark(FLOW3D_STAGE_UPDATE, st);
@@ -184,6 +198,21 @@ static int solve_level(const float* fx, const float* fy, const float* fz, const 
       std::swap(a0, b0);
       std::swap(a1, b1);
       std::swap(a2, b2);
+    }
+    if (outer_done) *outer_done = i + 1;
+    if (dg && dg->dev && dg->used < dg->capacity && inner > 0) {
+      if (tm) tm->mark(FLOW3D_STAGE_UPDATE, st);
+      double* rec = dg->dev + 2 * dg->used;
+      F3D_TRY(launch_update_norm(a0, a1, a2, b0, b1, b2, g, ZRange{0, g.d}, rec, dg->workspace, st));
+      if (dg->tol > 0.f) {  // adaptive stopping: the host has to see the value (one sync per outer iteration)
+        F3D_CUDA(cudaMemcpyAsync(dg->host + 2 * dg->used, rec, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        F3D_CUDA(cudaStreamSynchronize(st));
+        const double rms = std::sqrt(dg->host[2 * dg->used] / (3.0 * nvox));
+        ++dg->used;
+        if (rms < (double)dg->tol) break;
+      } else {
+        ++dg->used;
+      }
     }
   }
   if (tm) tm->mark(FLOW3D_STAGE_UPDATE, st);
@@ -215,6 +244,12 @@ struct flow3d_solver {
   flow3d_level_callback cb = nullptr;
   void* cb_user = nullptr;
   StageTimer timer;
+  // convergence diagnostics (off by default)
+  bool diag_enabled = false;
+  Diag diag;
+  std::vector<size_t> diag_level_outer;  // outer iterations run per level, coarsest first
+  std::vector<double> diag_records;      // {sum_sq, max_abs} per outer iteration, levels concatenated
+  std::vector<double> diag_level_voxels;
   float* buf(int i) const { return arena + (size_t)i * vol; }
 };
 
@@ -257,6 +292,25 @@ static int run_pyramid(flow3d_solver* s, const float* in0, const float* in1, siz
     F3D_CUDA(cudaMemcpy2DAsync(F1, s->ld * 4, in1, in_ld * 4, s->W * 4, s->H * s->D, cudaMemcpyDeviceToDevice, st));
   }
 
+  Diag* dg = nullptr;
+  s->diag_level_outer.clear();
+  s->diag_level_voxels.clear();
+  s->diag_records.clear();
+  if (s->diag_enabled) {
+    const size_t need = (size_t)(level + 1) * p->outer_iterations_count;
+    if (need > s->diag.capacity) {
+      if (s->diag.dev) cudaFree(s->diag.dev);
+      if (s->diag.host) cudaFreeHost(s->diag.host);
+      s->diag.dev = nullptr; s->diag.host = nullptr; s->diag.capacity = 0;
+      F3D_CUDA(cudaMalloc(&s->diag.dev, need * 2 * sizeof(double)));
+      F3D_CUDA(cudaMallocHost(&s->diag.host, need * 2 * sizeof(double)));
+      s->diag.capacity = need;
+    }
+    if (!s->diag.workspace) F3D_CUDA(cudaMalloc(&s->diag.workspace, update_norm_workspace_bytes()));
+    s->diag.used = 0;
+    dg = &s->diag;
+  }
+
   size_t prev[3] = {0, 0, 0};
   size_t prev_ld = 0;
   while (level >= 0) {  // :261
@@ -296,9 +350,14 @@ static int run_pyramid(flow3d_solver* s, const float* in0, const float* in1, siz
     F3D_TRY(launch_warp_derivatives(pf0, pf1, 0, g.d, u, v, w, g, ZRange{0, g.d}, h[0], h[1], h[2], fx, fy, fz,
                                     ft, st));
     // :372-417
+    size_t outer_done = 0;
     F3D_TRY(solve_level(fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, tdu, tdv, tdw, g, h,
                         p->outer_iterations_count, p->inner_iterations_count, p->equation_alpha,
-                        p->equation_smoothness, p->equation_data, st, tm));
+                        p->equation_smoothness, p->equation_data, st, tm, dg, &outer_done));
+    if (dg) {
+      s->diag_level_outer.push_back(p->inner_iterations_count > 0 ? outer_done : 0);
+      s->diag_level_voxels.push_back(nvox);
+    }
     // :420-438
     tm->mark(FLOW3D_STAGE_UPDATE, st, nvox);
     F3D_TRY(launch_add3(u, v, w, du, dv, dw, g, st));
@@ -328,6 +387,9 @@ static int run_pyramid(flow3d_solver* s, const float* in0, const float* in1, siz
       F3D_CUDA(cudaStreamSynchronize(st));
       s->cb(level + 1, cur, ld, u, v, w, s->cb_user);
     }
+  }
+  if (dg && dg->used) {  // bring the records home (after the last level; the caller's sync covers it)
+    F3D_CUDA(cudaMemcpyAsync(dg->host, dg->dev, dg->used * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
   }
   *out_u = u;
   *out_v = v;
@@ -745,6 +807,9 @@ int flow3d_solver_destroy(flow3d_solver* s) {
     if (s->ev[i]) cudaEventDestroy(s->ev[i]);
   if (s->stream) cudaStreamDestroy(s->stream);
   s->timer.destroy();
+  if (s->diag.dev) cudaFree(s->diag.dev);
+  if (s->diag.host) cudaFreeHost(s->diag.host);
+  if (s->diag.workspace) cudaFree(s->diag.workspace);
   if (s->arena) cudaFree(s->arena);
   delete s;
   return FLOW3D_OK;
@@ -842,6 +907,52 @@ int flow3d_solver_stage_times(flow3d_solver* s, float ms[FLOW3D_STAGE_COUNT],
     ms[i] = s->timer.ms[i];
     units[i] = s->timer.units[i];
     launches[i] = s->timer.launches[i];
+  }
+  return FLOW3D_OK;
+}
+
+size_t flow3d_update_norm_workspace_bytes(void) { return update_norm_workspace_bytes(); }
+
+int flow3d_update_norm(const float* a0, const float* a1, const float* a2, const float* b0,
+                       const float* b1, const float* b2, const size_t dims[3], size_t ld,
+                       const flow3d_zslab* slab, double* out_dev, void* workspace, void* stream) {
+  const void* ps[] = {a0, a1, a2, b0, b1, b2};
+  for (const void* p : ps) F3D_TRY(check_volume(p, dims, ld));
+  if (!out_dev || !workspace) return FLOW3D_ERR_INVALID_ARG;
+  F3D_TRY(check_slab(dims, slab));
+  const Dims g = make_slab_dims(dims, ld, slab);
+  return launch_update_norm(a0, a1, a2, b0, b1, b2, g, make_range(g, slab), out_dev, workspace, S(stream));
+}
+
+int flow3d_solver_set_diagnostics(flow3d_solver* s, int enable, float update_tolerance) {
+  if (!s) return FLOW3D_ERR_NOT_INITIALIZED;
+  if (!(update_tolerance >= 0.f)) return FLOW3D_ERR_INVALID_ARG;
+  s->diag_enabled = enable != 0;
+  s->diag.tol = enable ? update_tolerance : 0.f;
+  return FLOW3D_OK;
+}
+
+int flow3d_solver_diagnostics(flow3d_solver* s, size_t* n_levels, size_t* outer_per_level, double* rms,
+                              double* max_abs, size_t capacity, size_t* n_records) {
+  if (!s) return FLOW3D_ERR_NOT_INITIALIZED;
+  if (!n_levels || !n_records) return FLOW3D_ERR_INVALID_ARG;
+  F3D_CUDA(cudaSetDevice(s->device));
+  F3D_CUDA(cudaDeviceSynchronize());  // the record copy of a device-buffer solve may still be in flight
+  const size_t nl = s->diag_level_outer.size();
+  size_t total = 0;
+  for (size_t l = 0; l < nl; ++l) total += s->diag_level_outer[l];
+  if (total > s->diag.used) total = s->diag.used;
+  *n_levels = nl;
+  *n_records = total;
+  size_t k = 0;
+  for (size_t l = 0; l < nl; ++l) {
+    if (outer_per_level && l < capacity) outer_per_level[l] = s->diag_level_outer[l];
+    for (size_t i = 0; i < s->diag_level_outer[l] && k < total; ++i, ++k) {
+      if (k < capacity) {
+        if (rms) rms[k] = std::sqrt(s->diag.host[2 * k] / (3.0 * s->diag_level_voxels[l]));
+        if (max_abs) max_abs[k] = s->diag.host[2 * k + 1];
+      }
+    }
   }
   return FLOW3D_OK;
 }

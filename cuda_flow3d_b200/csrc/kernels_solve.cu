@@ -429,21 +429,44 @@ static int pick_lpr(int w, int vec) {
   return best;
 }
 
+// z chunking of a z-marching launch.  `resident` = CTAs of this kernel that fit on one SM.  Each CTA
+// marches `len` planes after a prologue of two; CTAs run in waves of sm_count*resident, and a partly
+// filled last wave costs as much as a full one, so the chunk count is chosen to minimise
+// waves * (len + prologue) instead of aiming at a fixed CTA count (512^3, VEC=4: 4 chunks = 6.9 waves
+// instead of 5 chunks = 8.65 waves).
 static void pick_grid(const Dims& g, ZRange zr, int vec, int lpr, int warps_per_block, dim3& grid, dim3& block,
-                      int& zchunk, int wx = 1) {
+                      int& zchunk, int wx = 1, int resident = 4) {
   const int nz = zr.end - zr.begin;
   block = dim3(32, warps_per_block, 1);
   const int rows_per_block = (warps_per_block / wx) * (32 / lpr);
   const int gx = (g.w + lpr * vec * wx - 1) / (lpr * vec * wx);
   const int gy = (g.h + rows_per_block - 1) / rows_per_block;
-  // enough z chunks for >= ~8 CTAs per SM in flight, but chunks of at least 8 planes (each chunk
-  // re-reads two planes of prologue)
   const long long per_plane = (long long)gx * gy;
-  const long long want = (long long)sm_count() * 16;
-  long long nchunks = (want + per_plane - 1) / per_plane;
-  if (nchunks < 1) nchunks = 1;
-  long long len = (nz + nchunks - 1) / nchunks;
   static const int min_chunk = env_int("FLOW3D_MIN_ZCHUNK", 8);
+  static const int model = env_int("FLOW3D_GRID_MODEL", 1);
+  long long len;
+  if (model) {
+    const long long slots = (long long)sm_count() * resident;
+    const int max_chunks = nz / min_chunk > 1 ? nz / min_chunk : 1;
+    double best = -1.0;
+    len = nz;
+    for (int n = 1; n <= max_chunks && n <= 256; ++n) {
+      const long long l = (nz + n - 1) / n;
+      const long long chunks = (nz + l - 1) / l;
+      const long long total = per_plane * chunks;
+      const long long waves = (total + slots - 1) / slots;
+      // a wave that is not the only one overlaps its neighbours a little: blend ceil and exact
+      const double w_eff = waves > 1 ? 0.75 * (double)waves + 0.25 * (double)total / (double)slots : 1.0;
+      const double cost = w_eff * (double)(l + 3);
+      if (best < 0.0 || cost < best * 0.995) { best = cost; len = l; }
+    }
+  } else {
+    // enough z chunks for >= ~16 CTAs per SM, but chunks of at least min_chunk planes
+    const long long want = (long long)sm_count() * 16;
+    long long nchunks = (want + per_plane - 1) / per_plane;
+    if (nchunks < 1) nchunks = 1;
+    len = (nz + nchunks - 1) / nchunks;
+  }
   if (len < min_chunk) len = min_chunk;
   if (len > nz) len = nz;
   if (len < 1) len = 1;
@@ -477,7 +500,7 @@ int launch_sweep(const float* fx, const float* fy, const float* fz, const float*
   static const int wx_env = env_int("FLOW3D_SWEEP_WX", 1);
   a.wx = (wx_env == 2 || wx_env == 4) && (rows % wx_env == 0) ? wx_env : 1;
   dim3 grid, block;
-  pick_grid(g, zr, vec, a.lpr, rows, grid, block, a.zchunk, a.wx);
+  pick_grid(g, zr, vec, a.lpr, rows, grid, block, a.zchunk, a.wx, vec == 4 ? 2 : 4);
   static const int rot = env_int("FLOW3D_SWEEP_ROT", 0), spec = env_int("FLOW3D_SWEEP_SPEC", 0);
   if (vec == 4) {
     if (rot && spec) sweep_kernel<4, 2, 1, 1><<<grid, block, 0, st>>>(a);
@@ -512,9 +535,9 @@ __device__ __forceinline__ float cdiff(const float* __restrict__ f, const float*
   return __fdiv_rn(t, two_h);
 }
 
-// value of ((f[p]-f[m]) + df[p]) - df[m]) / (2h) from already-loaded neighbours
-__device__ __forceinline__ float cdiff_r(float fp, float fm, float dfp, float dfm, ConstDiv two_h) {
-  return div_const(__fsub_rn(__fadd_rn(__fsub_rn(fp, fm), dfp), dfm), two_h);
+// ((f[p]-f[m]) + df[p]) - df[m] from already-loaded neighbours
+__device__ __forceinline__ float cnum(float fp, float fm, float dfp, float dfm) {
+  return __fsub_rn(__fadd_rn(__fsub_rn(fp, fm), dfp), dfm);
 }
 
 // Same structure as the sweep: one warp per row segment of 32*VEC voxels marching along z, the six
@@ -541,6 +564,7 @@ __global__ void __launch_bounds__(128) phi_ksi_kernel(const PhiKsiArgs a, int zc
   // divisors 2h are loop invariants: exact division through the double reciprocal (common.cuh)
   const ConstDiv thx = make_const_div(__fadd_rn(a.hx, a.hx)), thy = make_const_div(__fadd_rn(a.hy, a.hy)),
                  thz = make_const_div(__fadd_rn(a.hz, a.hz));
+  const bool fast_div = thx.fast && thy.fast && thz.fast;
 
   const float* F[6] = {a.u, a.du, a.v, a.dv, a.w, a.dw};
   Vec<VEC> prev[6], cur[6];
@@ -591,15 +615,34 @@ __global__ void __launch_bounds__(128) phi_ksi_kernel(const PhiKsiArgs a, int zc
     Vec<VEC> ophi, oksi;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      const float dux = cdiff_r(xp[0].v[i], xm[0].v[i], xp[1].v[i], xm[1].v[i], thx);
-      const float duy = cdiff_r(yp[0].v[i], ym[0].v[i], yp[1].v[i], ym[1].v[i], thy);
-      const float duz = cdiff_r(next[0].v[i], prev[0].v[i], next[1].v[i], prev[1].v[i], thz);
-      const float dvx = cdiff_r(xp[2].v[i], xm[2].v[i], xp[3].v[i], xm[3].v[i], thx);
-      const float dvy = cdiff_r(yp[2].v[i], ym[2].v[i], yp[3].v[i], ym[3].v[i], thy);
-      const float dvz = cdiff_r(next[2].v[i], prev[2].v[i], next[3].v[i], prev[3].v[i], thz);
-      const float dwx = cdiff_r(xp[4].v[i], xm[4].v[i], xp[5].v[i], xm[5].v[i], thx);
-      const float dwy = cdiff_r(yp[4].v[i], ym[4].v[i], yp[5].v[i], ym[5].v[i], thy);
-      const float dwz = cdiff_r(next[4].v[i], prev[4].v[i], next[5].v[i], prev[5].v[i], thz);
+      // numerators ((f[p]-f[m]) + df[p]) - df[m] of the nine central differences (solve_3d.cu:177-214)
+      float nm[9];
+      nm[0] = cnum(xp[0].v[i], xm[0].v[i], xp[1].v[i], xm[1].v[i]);
+      nm[1] = cnum(yp[0].v[i], ym[0].v[i], yp[1].v[i], ym[1].v[i]);
+      nm[2] = cnum(next[0].v[i], prev[0].v[i], next[1].v[i], prev[1].v[i]);
+      nm[3] = cnum(xp[2].v[i], xm[2].v[i], xp[3].v[i], xm[3].v[i]);
+      nm[4] = cnum(yp[2].v[i], ym[2].v[i], yp[3].v[i], ym[3].v[i]);
+      nm[5] = cnum(next[2].v[i], prev[2].v[i], next[3].v[i], prev[3].v[i]);
+      nm[6] = cnum(xp[4].v[i], xm[4].v[i], xp[5].v[i], xm[5].v[i]);
+      nm[7] = cnum(yp[4].v[i], ym[4].v[i], yp[5].v[i], ym[5].v[i]);
+      nm[8] = cnum(next[4].v[i], prev[4].v[i], next[5].v[i], prev[5].v[i]);
+      // quotients by the loop-invariant 2h through the FMA sequence (common.cuh).  One range test for
+      // the nine: the largest |numerator| bit pattern (NaN / Inf are the largest of all) must stay below
+      // 2^100.  Tiny numerators need no test here: a quotient below 2^-80 only ever enters the sum of
+      // squares below, where its square is an exact zero whichever way it was rounded.
+      unsigned big = 0u;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) big = max(big, __float_as_uint(nm[k]) & 0x7fffffffu);
+      float q[9];
+      if (fast_div && big <= 0x71800000u) {  // 2^100
+#pragma unroll
+        for (int k = 0; k < 9; ++k) q[k] = div_const_unchecked(nm[k], (k % 3 == 0) ? thx : (k % 3 == 1) ? thy : thz);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) q[k] = __fdiv_rn(nm[k], (k % 3 == 0) ? thx.c : (k % 3 == 1) ? thy.c : thz.c);
+      }
+      const float dux = q[0], duy = q[1], duz = q[2], dvx = q[3], dvy = q[4], dvz = q[5], dwx = q[6], dwy = q[7],
+                  dwz = q[8];
       // solve_3d.cu:217-218 as contracted by nvcc: mul(duy,duy) first, then one fma per term
       float acc = __fmul_rn(duy, duy);
       acc = __fmaf_rn(dux, dux, acc);
@@ -655,7 +698,7 @@ int launch_phi_ksi(const float* fx, const float* fy, const float* fz, const floa
   int zchunk = 0;
   static const int forced_lpr = env_int("FLOW3D_LPR", 0);
   const int lpr = (forced_lpr == 8 || forced_lpr == 16 || forced_lpr == 32) ? forced_lpr : pick_lpr(g.w, vec);
-  pick_grid(g, zr, vec, lpr, 4, grid, block, zchunk);
+  pick_grid(g, zr, vec, lpr, 4, grid, block, zchunk, 1, 5);
   if (vec == 4) phi_ksi_kernel<4><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end, lpr);
   else if (vec == 2) phi_ksi_kernel<2><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end, lpr);
   else phi_ksi_kernel<1><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end, lpr);

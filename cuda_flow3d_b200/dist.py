@@ -424,6 +424,24 @@ class ShardedFlowSolver:
         self.stats = {"sharded_levels": 0, "replicated_levels": 0, "exchanges": 0, "exchange_bytes": 0}
         self.profile = False      # record CUDA events around every batch of sweeps (CabiBackend only)
         self.sweep_events = []    # (start, end, voxel_sweeps, phi_ksi_voxels) per outer iteration
+        self.phase_marks = []     # (phase name, CUDA event): time until the next mark belongs to the phase
+
+    def _mark(self, name):
+        """profiling only: the device time from here to the next mark is attributed to phase `name`"""
+        if self.profile and self.be.name == "cabi":
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.phase_marks.append((name, e))
+
+    def phase_profile(self):
+        """{phase: milliseconds} of the recorded marks (device time, this rank); clears the record"""
+        out = {}
+        m = self.phase_marks
+        for (name, e0), (_, e1) in zip(m[:-1], m[1:]):
+            if name != "end":
+                out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
+        self.phase_marks = []
+        return out
 
     # ---- neighbour exchange of ghost planes -------------------------------------------------------
     def _exchange(self, fields, A, B, a, b, H, D):
@@ -511,6 +529,7 @@ class ShardedFlowSolver:
             self.stats["sharded_levels" if sharded else "replicated_levels"] += 1
 
             # ---- flow at this level: zeros, or box-prolongation of the previous level (:304-344) -----
+            self._mark("prolongation")
             flow = [Slab(be.zeros(w, hh, dl), A, d, w) for _ in range(3)]
             if prev is not None:
                 pdims, pflow, pv_lo, pv_hi = prev
@@ -519,7 +538,9 @@ class ShardedFlowSolver:
                 for c in range(3):
                     src = Slab(pflow[c].planes(s_lo, s_hi), s_lo, pdims[2], pdims[0])
                     be.resample(src, pdims, dims, A, a, b, out=flow[c])
+                self._mark("flow_ghost_exchange")
                 self._exchange([f.t for f in flow], A, B, a, b, H, d)
+            self._mark("level_frames")
             # ---- frames of this level, resampled from the replicated full-resolution frames -------------
             hz = h[2]
             wmax = be.absmax(flow[2]) if prev is not None else 0.0
@@ -544,12 +565,15 @@ class ShardedFlowSolver:
             # ---- warp + derivatives on every plane the solver touches ----------------------------------
             lo1 = A if A == 0 else A + 1
             hi1 = B if B == d else B - 1
+            self._mark("warp_derivs")
             terms = be.warp_terms(f0l, f1l, flow[0], flow[1], flow[2], h, lo1, hi1)
             # ---- solver (cuda_operation_solve.cpp:183-257) ----------------------------------------------
+            self._mark("alloc_zero")
             d_cur = [be.zeros(w, hh, dl) for _ in range(3)]
             d_alt = [be.zeros(w, hh, dl) for _ in range(3)]
             phi, ksi = be.zeros(w, hh, dl), be.zeros(w, hh, dl)
             for _ in range(outer):
+                self._mark("solver")
                 if prof:
                     e0 = torch.cuda.Event(enable_timing=True)
                     e0.record()
@@ -564,7 +588,9 @@ class ShardedFlowSolver:
                         units += w * hh * ((hi1 if hi1 == d else hi1 - j) - (lo1 if lo1 == 0 else lo1 + j))
                     self.sweep_events.append((e0, e1, units, w * hh * (hi1 - lo1)))
                 if sharded:
+                    self._mark("halo_exchange")
                     self._exchange(d_cur, A, B, a, b, H, d)
+            self._mark("update")
             # ---- u += du (:420-438), valid on the whole buffer because the last exchange refreshed du ----
             be.add3(flow, d_cur)
             # ---- median (:443-473) on everything whose +-r/2 neighbourhood is valid ---------------------
@@ -572,11 +598,13 @@ class ShardedFlowSolver:
             r2 = (r - 1 if (r % 2 == 0 and r > 1) else r) // 2
             m_lo = A if A == 0 else A + r2
             m_hi = B if B == d else B - r2
+            self._mark("median")
             for c in range(3):
                 be.median(flow[c], d_alt[c], r, m_lo, m_hi)
                 flow[c] = Slab(d_alt[c], A, d, w)
                 d_alt[c] = None
             prev = (dims, flow, m_lo, m_hi)
+            self._mark("end")
             if level_cb is not None:
                 level_cb(level, dims, (a, b), [be.to_numpy(f.planes(a, b), w) for f in flow])
         dims, flow, _, _ = prev

@@ -1,6 +1,7 @@
 // optical_flow.cpp -- OpticalFlowBase / OpticalFlowE with the reference's interface and messages
 // (src/optical_flow/optical_flow_base.cpp, optical_flow_e.cpp), implemented on the C ABI.
 #include <cstdio>
+#include <vector>
 
 #include "flow3d/cuda_utils.h"
 #include "flow3d/optical_flow_e.h"
@@ -98,6 +99,64 @@ void OpticalFlowE::ComputeFlow(Data3D& frame_0, Data3D& frame_1, Data3D& flow_u,
   }
   flow3d_solver_last_timing(solver_, last_ms_);
   std::printf("Total GPU computation time: % 4.4fs\n", last_ms_[0] / 1000.);
+}
+
+bool OpticalFlowE::SetDiagnostics(bool enable, float update_tolerance) {
+  if (!solver_) return false;
+  last_status_ = flow3d_solver_set_diagnostics(solver_, enable ? 1 : 0, update_tolerance);
+  return last_status_ == FLOW3D_OK;
+}
+
+void OpticalFlowE::PrintDiagnostics() const {
+  if (!solver_) return;
+  size_t nl = 0, nr = 0;
+  if (flow3d_solver_diagnostics(solver_, &nl, nullptr, nullptr, nullptr, 0, &nr) != FLOW3D_OK || nl == 0) return;
+  const size_t cap = nl > nr ? nl : nr;
+  std::vector<size_t> per(cap);
+  std::vector<double> rms(cap), mx(cap);
+  if (flow3d_solver_diagnostics(solver_, &nl, per.data(), rms.data(), mx.data(), cap, &nr) != FLOW3D_OK) return;
+  size_t k = 0;
+  for (size_t l = 0; l < nl; ++l) {
+    if (per[l] > 0)
+      std::printf("level %2zu: outer %3zu  rms update %.3e -> %.3e  max %.3e\n", nl - 1 - l, per[l], rms[k],
+                  rms[k + per[l] - 1], mx[k + per[l] - 1]);
+    k += per[l];
+  }
+}
+
+bool OpticalFlowE::WarpFrame(Data3D& frame_0, Data3D& frame_1, Data3D& flow_u, Data3D& flow_v, Data3D& flow_w,
+                             Data3D& warped, Data3D* abs_error) {
+  Data3D* vols[6] = {&frame_0, &frame_1, &flow_u, &flow_v, &flow_w, &warped};
+  const size_t W = frame_0.Width(), H = frame_0.Height(), D = frame_0.Depth();
+  for (Data3D* v : vols)
+    if (v->Width() != W || v->Height() != H || v->Depth() != D || !v->DataPtr()) return false;
+  if (abs_error && (abs_error->Width() != W || abs_error->Height() != H || abs_error->Depth() != D)) return false;
+  const size_t dims[3] = {W, H, D};
+  const size_t ld = flow3d_aligned_ld(W);
+  const size_t bytes = ld * H * D * sizeof(float);
+  void* dev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int rc = flow3d_set_device(device_);
+  for (int i = 0; i < 6 && rc == FLOW3D_OK; ++i) rc = flow3d_malloc(&dev[i], bytes);
+  for (int i = 0; i < 5 && rc == FLOW3D_OK; ++i)
+    rc = flow3d_upload(vols[i]->DataPtr(), static_cast<float*>(dev[i]), dims, ld, nullptr);
+  const float h[3] = {1.f, 1.f, 1.f};  // full resolution
+  if (rc == FLOW3D_OK)
+    rc = flow3d_warp(static_cast<float*>(dev[0]), static_cast<float*>(dev[1]), static_cast<float*>(dev[2]),
+                     static_cast<float*>(dev[3]), static_cast<float*>(dev[4]), dims, ld, h,
+                     static_cast<float*>(dev[5]), nullptr);
+  if (rc == FLOW3D_OK) rc = flow3d_download(static_cast<float*>(dev[5]), warped.DataPtr(), dims, ld, nullptr);
+  if (rc == FLOW3D_OK) rc = flow3d_stream_synchronize(nullptr);
+  for (void* p : dev)
+    if (p) flow3d_free(p);
+  last_status_ = rc;
+  if (rc != FLOW3D_OK) return false;
+  if (abs_error) {
+    const float* a = warped.DataPtr();
+    const float* b = frame_0.DataPtr();
+    float* e = abs_error->DataPtr();
+    for (size_t i = 0; i < W * H * D; ++i) e[i] = a[i] > b[i] ? a[i] - b[i] : b[i] - a[i];
+  }
+  return true;
 }
 
 void OpticalFlowE::Destroy() {

@@ -28,6 +28,16 @@ class OpticalFlowE : public OpticalFlowBase {
   float last_total_ms() const { return last_ms_[0]; }   // H2D + levels + D2H (the reference's bracket)
   float last_device_ms() const { return last_ms_[1]; }  // levels only
   void SetDevice(int device) { device_ = device; }      // before Initialize(); default 0
+  // Convergence diagnostics (flow3d_solver_set_diagnostics): record the Jacobi update norm per level
+  // and outer iteration; update_tolerance > 0 stops a level early (results then differ from the
+  // reference's fixed iteration count).  Call after Initialize().
+  bool SetDiagnostics(bool enable, float update_tolerance = 0.f);
+  // prints "level <k>: outer <n> rms <first> -> <last> max <last>" for the last ComputeFlow
+  void PrintDiagnostics() const;
+  // Registered volume: frame_1 warped back by the flow (what the reference's disabled debug block
+  // optical_flow_e.cpp:535-571 wrote out), and optionally |warped - frame_0| as an error map.
+  bool WarpFrame(Data3D& frame_0, Data3D& frame_1, Data3D& flow_u, Data3D& flow_v, Data3D& flow_w,
+                 Data3D& warped, Data3D* abs_error = nullptr);
 
  private:
   flow3d_solver* solver_ = nullptr;

@@ -274,6 +274,27 @@ typedef void (*flow3d_level_callback)(int level, const size_t dims[3], size_t ld
                                       void* user);
 int flow3d_solver_set_level_callback(flow3d_solver* s, flow3d_level_callback cb, void* user);
 
+/* ---- convergence diagnostics (NOT part of the reference's path) ------------
+ * The reference runs a fixed number of sweeps and never evaluates a residual
+ * (src/cuda_operations/entire_data/cuda_operation_solve.cpp:194-257).  flow3d_update_norm measures
+ * the last Jacobi update: out_dev[0] = sum over voxels and the three components of (a - b)^2,
+ * out_dev[1] = max |a - b| (NaN if any), over the slab's [z_begin, z_end) (whole volume if NULL).
+ * Deterministic (fixed-order fold of per-block partials; warp shuffles inside a block).
+ * workspace: flow3d_update_norm_workspace_bytes() bytes of device memory. */
+size_t flow3d_update_norm_workspace_bytes(void);
+int flow3d_update_norm(const float* a0, const float* a1, const float* a2, const float* b0,
+                       const float* b1, const float* b2, const size_t dims[3], size_t ld,
+                       const flow3d_zslab* slab, double* out_dev, void* workspace, void* stream);
+/* enable != 0: every compute call records, per level and outer iteration, the update norm between the
+ * last two sweeps.  update_tolerance > 0 additionally stops a level's outer loop once the RMS update
+ * (voxel units) drops below it -- an opt-in fast mode whose results differ from the reference's. */
+int flow3d_solver_set_diagnostics(flow3d_solver* s, int enable, float update_tolerance);
+/* records of the last compute call, levels coarsest first: *n_levels, outer_per_level[l] = outer
+ * iterations run on level l, rms[k] / max_abs[k] for the k-th record overall (k < *n_records).
+ * Arrays may be NULL; at most `capacity` entries are written to each. */
+int flow3d_solver_diagnostics(flow3d_solver* s, size_t* n_levels, size_t* outer_per_level, double* rms,
+                              double* max_abs, size_t capacity, size_t* n_records);
+
 /* ---- synthetic test volumes ---------------------------------
  * Analytic texture pair with a known rigid motion, generated on the device in double precision.
  * z0/nz select a z-slab (for sharded generation); out_* may be NULL.  truth_* receive the
