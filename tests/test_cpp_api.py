@@ -65,3 +65,34 @@ def test_cli_f32_vtk_and_params(tmp_path):
     r = subprocess.run([CLI, "--dims", "28", "20", "13", "--frame0", str(tmp_path / "a.raw"), "--frame1",
                         str(tmp_path / "b.raw"), "--f32"], capture_output=True, text=True)
     assert r.returncode == 2 and "wrong dimensions" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cli_diagnostics_and_warped_outputs(gpu, tmp_path):
+    """update-norm report, early stopping, registered volume + error map"""
+    f0, f1, _ = gpu.ops.synth_pair(40, 36, 32, truth=False)
+    f0.tofile(tmp_path / "a.raw")
+    f1.tofile(tmp_path / "b.raw")
+    base = [CLI, "--dims", "40", "36", "32", "--frame0", str(tmp_path / "a.raw"), "--frame1", str(tmp_path / "b.raw"),
+            "--f32", "--param", "warp_levels_count=4", "--param", "warp_scale_factor=0.8", "--param",
+            "outer_iterations_count=6"]
+    r = subprocess.run(base + ["--out", str(tmp_path / "p"), "--diagnostics", "--warped", str(tmp_path / "w")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.startswith("level ")]
+    assert len(lines) == 4 and all("outer   6" in l for l in lines)
+    warped = np.fromfile(tmp_path / "w_warped.raw", np.float32).reshape(32, 36, 40)
+    err = np.fromfile(tmp_path / "w_error.raw", np.float32).reshape(32, 36, 40)
+    flow = [np.fromfile(tmp_path / ("p_%s.raw" % c), np.float32).reshape(32, 36, 40) for c in "uvw"]
+    # the registered frame is exactly the stage function's warp of frame 1 by the final flow
+    want = gpu.ops.warp(f0, f1, flow[0], flow[1], flow[2], (1.0, 1.0, 1.0))
+    assert np.array_equal(warped, want)
+    assert np.array_equal(err, np.abs(warped - f0))
+    # registration helps: the warped frame is closer to frame 0 than frame 1 was
+    inner = (slice(4, -4),) * 3
+    assert np.abs(warped - f0)[inner].mean() < 0.5 * np.abs(f1 - f0)[inner].mean()
+    # a (huge) tolerance stops every level after its first outer iteration
+    r = subprocess.run(base + ["--tolerance", "1e9"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.startswith("level ")]
+    assert len(lines) == 4 and all("outer   1" in l for l in lines)
