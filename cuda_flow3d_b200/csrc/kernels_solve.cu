@@ -9,10 +9,20 @@
 // precomputed image derivatives) is new.  A sensitivity study shows that merely changing
 // FMA contraction moves the final 128^3 flow by up to 9e-3 voxel, so this is what the 1e-3 gate needs.
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
 
 #include "common.cuh"
 
 namespace f3d {
+
+#define F3D_TRY_RC(expr)                \
+  do {                                 \
+    int rc_ = (expr);                  \
+    if (rc_ != FLOW3D_OK) return rc_;  \
+  } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // small vector helpers
@@ -435,7 +445,7 @@ static int pick_lpr(int w, int vec) {
 // waves * (len + prologue) instead of aiming at a fixed CTA count (512^3, VEC=4: 4 chunks = 6.9 waves
 // instead of 5 chunks = 8.65 waves).
 static void pick_grid(const Dims& g, ZRange zr, int vec, int lpr, int warps_per_block, dim3& grid, dim3& block,
-                      int& zchunk, int wx = 1, int resident = 4) {
+                      int& zchunk, int wx = 1, int resident = 4, int forced_len = 0) {
   const int nz = zr.end - zr.begin;
   block = dim3(32, warps_per_block, 1);
   const int rows_per_block = (warps_per_block / wx) * (32 / lpr);
@@ -443,8 +453,15 @@ static void pick_grid(const Dims& g, ZRange zr, int vec, int lpr, int warps_per_
   const int gy = (g.h + rows_per_block - 1) / rows_per_block;
   const long long per_plane = (long long)gx * gy;
   static const int min_chunk = env_int("FLOW3D_MIN_ZCHUNK", 8);
-  static const int model = env_int("FLOW3D_GRID_MODEL", 1);
+  static const int model = env_int("FLOW3D_GRID_MODEL", 0);
   long long len;
+  if (forced_len > 0) {
+    len = forced_len;
+    if (len > nz) len = nz;
+    zchunk = (int)len;
+    grid = dim3(gx, gy, (nz + zchunk - 1) / zchunk);
+    return;
+  }
   if (model) {
     const long long slots = (long long)sm_count() * resident;
     const int max_chunks = nz / min_chunk > 1 ? nz / min_chunk : 1;
@@ -483,14 +500,89 @@ static int pick_vec(const Dims& g) {
   return 1;
 }
 
-int launch_sweep(const float* fx, const float* fy, const float* fz, const float* ft,
-                 const float* u, const float* v, const float* w, const float* du, const float* dv,
-                 const float* dw, const float* phi, const float* ksi, Dims g, ZRange zr, float hx,
-                 float hy, float hz, float alpha, float* odu, float* odv, float* odw, cudaStream_t st) {
-  if (zr.end <= zr.begin) return FLOW3D_OK;
-  SweepArgs a{fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, odu, odv, odw, g, hx, hy, hz, alpha, 0, 0,
-              zr.begin, zr.end, 32, 0, 1};
-  const int vec = pick_vec(g);
+// ------------------------------------------------------------------------------------------------
+// Launch-shape autotuner.  The z-marching kernels give identical results for every vector width and
+// every z chunking, and which shape is fastest depends on the level size in ways a closed-form model
+// misses (wave quantisation at small levels, load balance across the two dies at large ones: measured,
+// profiles/).  So the first launch for a (kernel, w, h, depth) runs each candidate shape a few times on
+// the caller's own arguments (out != in, so repeating a launch is idempotent), times them with CUDA
+// events on the caller's stream and caches the winner; every later launch is a map lookup.
+// FLOW3D_AUTOTUNE=0 keeps the static heuristic.
+// ------------------------------------------------------------------------------------------------
+struct TuneKey {
+  int kernel, w, h, ld, nzq;
+  bool operator<(const TuneKey& o) const {
+    return std::tie(kernel, w, h, ld, nzq) < std::tie(o.kernel, o.w, o.h, o.ld, o.nzq);
+  }
+};
+struct TuneCfg {
+  int vec;
+  int nchunks;  // z chunks (0 = static heuristic)
+};
+static std::mutex g_tune_mu;
+static std::map<TuneKey, TuneCfg> g_tune;
+
+static bool autotune_enabled() {
+  static const int on = env_int("FLOW3D_AUTOTUNE", 1);
+  return on != 0;
+}
+// whole-level launches are keyed by their exact depth; slab launches (ranges that shrink sweep by
+// sweep) share a key per 16 planes
+static TuneKey tune_key(int kernel, const Dims& g, ZRange zr) {
+  const int nz = zr.end - zr.begin;
+  const bool whole = zr.begin == 0 && zr.end == g.d && g.d == g.dg;
+  return TuneKey{kernel, g.w, g.h, g.ld, whole ? -nz : (nz + 15) / 16};
+}
+static inline int chunk_len(int nz, int nchunks) {
+  if (nchunks < 1) nchunks = 1;
+  int len = (nz + nchunks - 1) / nchunks;
+  return len < 1 ? 1 : len;
+}
+// chunk counts around the static heuristic's choice n0, chunks of at least 4 planes
+static void chunk_candidates(int nz, long long per_plane, std::vector<int>& out) {
+  const long long want = (long long)sm_count() * 16;
+  long long n0 = (want + per_plane - 1) / per_plane;
+  if (n0 < 1) n0 = 1;
+  const double f[] = {0.125, 0.25, 0.5, 0.75, 1.0, 1.5, 2.0, 3.0};
+  out.clear();
+  int last_len = -1;
+  for (double k : f) {
+    long long n = (long long)(n0 * k + 0.5);
+    if (n < 1) n = 1;
+    int len = chunk_len(nz, (int)(n > nz ? nz : n));
+    if (len < 4) len = nz < 4 ? nz : 4;
+    const int chunks = (nz + len - 1) / len;
+    if (len == last_len) continue;
+    bool dup = false;
+    for (int c : out) dup = dup || c == chunks;
+    if (!dup) out.push_back(chunks);
+    last_len = len;
+  }
+}
+template <class Launch>
+static int tune_pick(const std::vector<TuneCfg>& cands, Launch&& launch, cudaStream_t st, TuneCfg* best) {
+  cudaEvent_t e0, e1;
+  if (cudaEventCreate(&e0) != cudaSuccess) return FLOW3D_ERR_CUDA;
+  if (cudaEventCreate(&e1) != cudaSuccess) { cudaEventDestroy(e0); return FLOW3D_ERR_CUDA; }
+  int rc = launch(cands[0]);  // warm
+  float best_ms = -1.f;
+  const int reps = 3;
+  for (size_t i = 0; i < cands.size() && rc == FLOW3D_OK; ++i) {
+    cudaEventRecord(e0, st);
+    for (int r = 0; r < reps && rc == FLOW3D_OK; ++r) rc = launch(cands[i]);
+    cudaEventRecord(e1, st);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { rc = FLOW3D_ERR_CUDA; break; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (best_ms < 0.f || ms < best_ms) { best_ms = ms; *best = cands[i]; }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return rc;
+}
+
+static int launch_sweep_cfg(SweepArgs a, const Dims& g, ZRange zr, TuneCfg cfg, cudaStream_t st) {
+  const int vec = cfg.vec;
   static const int pf = env_int("FLOW3D_SWEEP_PF", 2);
   static const int rows = env_int("FLOW3D_SWEEP_ROWS", 4);
   static const int forced_lpr = env_int("FLOW3D_LPR", 0);
@@ -500,7 +592,8 @@ int launch_sweep(const float* fx, const float* fy, const float* fz, const float*
   static const int wx_env = env_int("FLOW3D_SWEEP_WX", 1);
   a.wx = (wx_env == 2 || wx_env == 4) && (rows % wx_env == 0) ? wx_env : 1;
   dim3 grid, block;
-  pick_grid(g, zr, vec, a.lpr, rows, grid, block, a.zchunk, a.wx, vec == 4 ? 2 : 4);
+  pick_grid(g, zr, vec, a.lpr, rows, grid, block, a.zchunk, a.wx, vec == 4 ? 2 : 4,
+            cfg.nchunks > 0 ? chunk_len(zr.end - zr.begin, cfg.nchunks) : 0);
   static const int rot = env_int("FLOW3D_SWEEP_ROT", 0), spec = env_int("FLOW3D_SWEEP_SPEC", 0);
   if (vec == 4) {
     if (rot && spec) sweep_kernel<4, 2, 1, 1><<<grid, block, 0, st>>>(a);
@@ -514,6 +607,47 @@ int launch_sweep(const float* fx, const float* fy, const float* fz, const float*
   }
   count_launch();
   return check_launch("sweep_kernel");
+}
+
+int launch_sweep(const float* fx, const float* fy, const float* fz, const float* ft,
+                 const float* u, const float* v, const float* w, const float* du, const float* dv,
+                 const float* dw, const float* phi, const float* ksi, Dims g, ZRange zr, float hx,
+                 float hy, float hz, float alpha, float* odu, float* odv, float* odw, cudaStream_t st) {
+  if (zr.end <= zr.begin) return FLOW3D_OK;
+  SweepArgs a{fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, odu, odv, odw, g, hx, hy, hz, alpha, 0, 0,
+              zr.begin, zr.end, 32, 0, 1};
+  const int nz = zr.end - zr.begin;
+  TuneCfg cfg{pick_vec(g), 0};
+  static const int forced_vec = env_int("FLOW3D_SWEEP_VEC", 0);
+  if (autotune_enabled() && forced_vec == 0 && nz >= 8 && (long long)g.w * g.h * nz >= 32768) {
+    const TuneKey key = tune_key(0, g, zr);
+    bool have;
+    {
+      std::lock_guard<std::mutex> lk(g_tune_mu);
+      auto it = g_tune.find(key);
+      have = it != g_tune.end();
+      if (have) cfg = it->second;
+    }
+    if (!have) {
+      std::vector<TuneCfg> cands;
+      std::vector<int> chunks;
+      int vecs[2] = {cfg.vec, 0};
+      if (cfg.vec == 4) vecs[1] = 2;
+      else if (cfg.vec == 2 && g.w >= 128) vecs[1] = 4;
+      for (int vi = 0; vi < 2; ++vi) {
+        const int vec = vecs[vi];
+        if (!vec) continue;
+        const int lpr = pick_lpr(g.w, vec);
+        const long long per_plane = (long long)((g.w + lpr * vec - 1) / (lpr * vec)) * ((g.h + 4 * (32 / lpr) - 1) / (4 * (32 / lpr)));
+        chunk_candidates(nz, per_plane, chunks);
+        for (int c : chunks) cands.push_back(TuneCfg{vec, c});
+      }
+      F3D_TRY_RC(tune_pick(cands, [&](TuneCfg c) { return launch_sweep_cfg(a, g, zr, c, st); }, st, &cfg));
+      std::lock_guard<std::mutex> lk(g_tune_mu);
+      g_tune[key] = cfg;
+    }
+  }
+  return launch_sweep_cfg(a, g, zr, cfg, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -684,6 +818,21 @@ __global__ void __launch_bounds__(128) phi_ksi_kernel(const PhiKsiArgs a, int zc
   }
 }
 
+static int launch_phi_ksi_cfg(const PhiKsiArgs& a, const Dims& g, ZRange zr, TuneCfg cfg, cudaStream_t st) {
+  static const int pf = env_int("FLOW3D_PHIKSI_PF", 2);
+  const int vec = cfg.vec;
+  dim3 grid, block;
+  int zchunk = 0;
+  static const int forced_lpr = env_int("FLOW3D_LPR", 0);
+  const int lpr = (forced_lpr == 8 || forced_lpr == 16 || forced_lpr == 32) ? forced_lpr : pick_lpr(g.w, vec);
+  pick_grid(g, zr, vec, lpr, 4, grid, block, zchunk, 1, 5, cfg.nchunks > 0 ? chunk_len(zr.end - zr.begin, cfg.nchunks) : 0);
+  if (vec == 4) phi_ksi_kernel<4><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end, lpr);
+  else if (vec == 2) phi_ksi_kernel<2><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end, lpr);
+  else phi_ksi_kernel<1><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end, lpr);
+  count_launch();
+  return check_launch("phi_ksi_kernel");
+}
+
 int launch_phi_ksi(const float* fx, const float* fy, const float* fz, const float* ft,
                    const float* u, const float* v, const float* w, const float* du,
                    const float* dv, const float* dw, Dims g, ZRange zr, float hx, float hy, float hz,
@@ -691,19 +840,32 @@ int launch_phi_ksi(const float* fx, const float* fy, const float* fz, const floa
   if (zr.end <= zr.begin) return FLOW3D_OK;
   PhiKsiArgs a{fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, g, hx, hy, hz, eps_s, eps_d};
   static const int forced = env_int("FLOW3D_PHIKSI_VEC", 0);
-  static const int pf = env_int("FLOW3D_PHIKSI_PF", 2);
-  int vec = (g.w >= 48) ? 2 : 1;  // measured: VEC=2 (114 regs, 16 warps/SM) beats VEC=4 (191 regs)
+  int vec = (g.w >= 48) ? 2 : 1;  // measured: VEC=2 (16+ warps/SM) beats VEC=4 (191 regs)
   if (forced == 1 || forced == 2 || forced == 4) vec = forced;
-  dim3 grid, block;
-  int zchunk = 0;
-  static const int forced_lpr = env_int("FLOW3D_LPR", 0);
-  const int lpr = (forced_lpr == 8 || forced_lpr == 16 || forced_lpr == 32) ? forced_lpr : pick_lpr(g.w, vec);
-  pick_grid(g, zr, vec, lpr, 4, grid, block, zchunk, 1, 5);
-  if (vec == 4) phi_ksi_kernel<4><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end, lpr);
-  else if (vec == 2) phi_ksi_kernel<2><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end, lpr);
-  else phi_ksi_kernel<1><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end, lpr);
-  count_launch();
-  return check_launch("phi_ksi_kernel");
+  TuneCfg cfg{vec, 0};
+  const int nz = zr.end - zr.begin;
+  if (autotune_enabled() && forced == 0 && nz >= 8 && (long long)g.w * g.h * nz >= 32768) {
+    const TuneKey key = tune_key(1, g, zr);
+    bool have;
+    {
+      std::lock_guard<std::mutex> lk(g_tune_mu);
+      auto it = g_tune.find(key);
+      have = it != g_tune.end();
+      if (have) cfg = it->second;
+    }
+    if (!have) {
+      std::vector<TuneCfg> cands;
+      std::vector<int> chunks;
+      const int lpr = pick_lpr(g.w, vec);
+      const long long per_plane = (long long)((g.w + lpr * vec - 1) / (lpr * vec)) * ((g.h + 4 * (32 / lpr) - 1) / (4 * (32 / lpr)));
+      chunk_candidates(nz, per_plane, chunks);
+      for (int c : chunks) cands.push_back(TuneCfg{vec, c});
+      F3D_TRY_RC(tune_pick(cands, [&](TuneCfg c) { return launch_phi_ksi_cfg(a, g, zr, c, st); }, st, &cfg));
+      std::lock_guard<std::mutex> lk(g_tune_mu);
+      g_tune[key] = cfg;
+    }
+  }
+  return launch_phi_ksi_cfg(a, g, zr, cfg, st);
 }
 
 // ------------------------------------------------------------------------------------------------
