@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <utility>
@@ -41,6 +42,14 @@ int sm_count() {
       cached = 148;
   }
   return cached;
+}
+
+static bool fuse_ksi() {
+  static const int on = [] {
+    const char* e = getenv("FLOW3D_FUSE_KSI");
+    return (e && *e) ? atoi(e) : 1;
+  }();
+  return on != 0;
 }
 
 // Stage timer: mark(tag) records an event; the time until the next mark belongs to `tag`.
@@ -188,13 +197,17 @@ static int solve_level(const float* fx, const float* fy, const float* fz, const 
   F3D_CUDA(cudaMemsetAsync(dw, 0, bytes, st));
   float *a0 = du, *a1 = dv, *a2 = dw, *b0 = tdu, *b1 = tdv, *b2 = tdw;
   for (size_t i = 0; i < outer; ++i) {  // :194-257
+    // The robust weights of compute_phi_ksi_3d are split: phi (needs neighbours) in its own launch, ksi
+    // (pointwise in the iterate) inside the first sweep, which reads every operand of it anyway --
+    // same operations, five fewer words of traffic per voxel and outer iteration.
+    const bool fuse = fuse_ksi() && inner > 0;
     if (tm) tm->mark(FLOW3D_STAGE_PHI_KSI, st, nvox);
     F3D_TRY(launch_phi_ksi(fx, fy, fz, ft, u, v, w, a0, a1, a2, g, ZRange{0, g.d}, h[0], h[1], h[2], eps_s,
-                           eps_d, phi, ksi, st));
+                           eps_d, phi, fuse ? nullptr : ksi, st));
     if (tm) tm->mark(FLOW3D_STAGE_SWEEP, st, nvox * (double)inner);
     for (size_t j = 0; j < inner; ++j) {
       F3D_TRY(launch_sweep(fx, fy, fz, ft, u, v, w, a0, a1, a2, phi, ksi, g, ZRange{0, g.d}, h[0], h[1], h[2],
-                           alpha, b0, b1, b2, st));
+                           alpha, b0, b1, b2, st, (fuse && j == 0) ? ksi : nullptr, eps_d));
       std::swap(a0, b0);
       std::swap(a1, b1);
       std::swap(a2, b2);
@@ -721,13 +734,16 @@ int flow3d_outer_iteration_slab(const float* fx, const float* fy, const float* f
   const ZRange r0 = make_range(g, slab);
   const bool lo_face = (g.z0g + r0.begin) == 0, hi_face = (g.z0g + r0.end) == g.dg;
   cudaStream_t st = S(stream);
+  // ksi is pointwise in the iterate, so the first sweep computes it (every later sweep of the iteration
+  // works inside the first one's range)
+  const bool fuse = fuse_ksi() && inner > 0;
   F3D_TRY(launch_phi_ksi(fx, fy, fz, ft, u, v, w, du, dv, dw, g, r0, h[0], h[1], h[2], eps_smooth, eps_data, phi,
-                         ksi, st));
+                         fuse ? nullptr : ksi, st));
   float *a0 = du, *a1 = dv, *a2 = dw, *b0 = tdu, *b1 = tdv, *b2 = tdw;
   for (size_t j = 1; j <= inner; ++j) {
     ZRange r{lo_face ? r0.begin : r0.begin + (int)j, hi_face ? r0.end : r0.end - (int)j};
     F3D_TRY(launch_sweep(fx, fy, fz, ft, u, v, w, a0, a1, a2, phi, ksi, g, r, h[0], h[1], h[2], alpha, b0, b1, b2,
-                         st));
+                         st, (fuse && j == 1) ? ksi : nullptr, eps_data));
     std::swap(a0, b0);
     std::swap(a1, b1);
     std::swap(a2, b2);

@@ -1,6 +1,8 @@
 // kernels_pyramid.cu -- Gaussian pre-blur and box resampling (pyramid construction, flow
 // prolongation) for sm_100a.  Arithmetic is transcribed operation by operation from the reference
 // kernels' PTX (see kernels_solve.cu for the contract).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace f3d {
@@ -94,12 +96,103 @@ __global__ void __launch_bounds__(256) resample_axis_kernel(const float* __restr
   out[(long long)z * go.ps + (long long)y * go.ld + x] = __fmul_rn(norm, value);
 }
 
+// Tap geometry of one output index (resample_3d.cu:41-48), shared by the kernels below
+struct ResampleTaps {
+  float delta, norm, left_f, right_f, first;
+  int left_i, cnt;
+};
+__device__ __forceinline__ ResampleTaps resample_taps(unsigned o, unsigned long long a, unsigned long long b) {
+  ResampleTaps t;
+  const float fa = (float)a, fb = (float)b;
+  t.delta = __fdiv_rn(fa, fb);
+  t.norm = __fdiv_rn(fb, fa);
+  t.left_f = __fmul_rn((float)o, t.delta);
+  t.right_f = __fmul_rn((float)(o + 1u), t.delta);
+  t.left_i = (int)floorf(t.left_f);
+  const int right_i = (int)fminf(fa, (float)(unsigned long long)ceilf(t.right_f));
+  t.cnt = right_i - t.left_i;
+  t.first = __fsub_rn((float)(t.left_i + 1), t.left_f);
+  return t;
+}
+__device__ __forceinline__ float resample_frac(const ResampleTaps& t, int j) {
+  float frac = 1.f;
+  if (j == 0) frac = t.first;
+  if (j == t.cnt - 1) frac = __fsub_rn(t.right_f, (float)(t.left_i + j));
+  if (t.cnt == 1) frac = t.delta;
+  return frac;
+}
+
+// y / z pass, four consecutive x per thread: every tap is one float4 load (rows are 16-byte aligned and
+// padded to a multiple of four floats), and the first three taps are loaded before the first fma so
+// the loads overlap.  Same per-element arithmetic and tap order as resample_axis_kernel.
+template <int AXIS>
+__global__ void __launch_bounds__(256) resample_axis_vec4_kernel(const float* __restrict__ in, Dims gi,
+                                                                 float* __restrict__ out, Dims go, int zs) {
+  static_assert(AXIS == 1 || AXIS == 2, "x pass is scalar");
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int z = zs + blockIdx.z;
+  if (x >= go.w || y >= go.h) return;
+  const unsigned o = AXIS == 1 ? y : (go.z0g + z);
+  const ResampleTaps t = resample_taps(o, AXIS == 1 ? gi.h : gi.dg, AXIS == 1 ? go.h : go.dg);
+  const long long base = AXIS == 1 ? ((long long)z * gi.ps + (long long)t.left_i * gi.ld + x)
+                                   : ((long long)(t.left_i - gi.z0g) * gi.ps + (long long)y * gi.ld + x);
+  const long long stride = AXIS == 1 ? (long long)gi.ld : gi.ps;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto tap = [&](int j) { return __ldg(reinterpret_cast<const float4*>(in + base + (long long)j * stride)); };
+  auto fma4 = [&](float f, const float4& v) {
+    acc.x = __fmaf_rn(f, v.x, acc.x); acc.y = __fmaf_rn(f, v.y, acc.y);
+    acc.z = __fmaf_rn(f, v.z, acc.z); acc.w = __fmaf_rn(f, v.w, acc.w);
+  };
+  const int cnt = t.cnt;
+  const float4 v0 = tap(0);
+  const float4 v1 = tap(cnt > 1 ? 1 : 0);
+  const float4 v2 = tap(cnt > 2 ? 2 : 0);
+  if (cnt > 0) fma4(resample_frac(t, 0), v0);
+  if (cnt > 1) fma4(resample_frac(t, 1), v1);
+  if (cnt > 2) fma4(resample_frac(t, 2), v2);
+  for (int j = 3; j < cnt; ++j) fma4(resample_frac(t, j), tap(j));
+  float4 r;
+  r.x = __fmul_rn(t.norm, acc.x); r.y = __fmul_rn(t.norm, acc.y);
+  r.z = __fmul_rn(t.norm, acc.z); r.w = __fmul_rn(t.norm, acc.w);
+  *reinterpret_cast<float4*>(out + (long long)z * go.ps + (long long)y * go.ld + x) = r;
+}
+
+// x pass: one output per thread, the first three taps loaded up front (fine levels have <= 3 taps)
+__global__ void __launch_bounds__(256) resample_x_kernel(const float* __restrict__ in, Dims gi,
+                                                         float* __restrict__ out, Dims go, int zs) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int z = zs + blockIdx.z;
+  if (x >= go.w || y >= go.h) return;
+  const ResampleTaps t = resample_taps((unsigned)x, gi.w, go.w);
+  const float* p = in + (long long)z * gi.ps + (long long)y * gi.ld + t.left_i;
+  const int cnt = t.cnt;
+  const float v0 = __ldg(p);
+  const float v1 = __ldg(p + (cnt > 1 ? 1 : 0));
+  const float v2 = __ldg(p + (cnt > 2 ? 2 : 0));
+  float value = 0.f;
+  if (cnt > 0) value = __fmaf_rn(resample_frac(t, 0), v0, value);
+  if (cnt > 1) value = __fmaf_rn(resample_frac(t, 1), v1, value);
+  if (cnt > 2) value = __fmaf_rn(resample_frac(t, 2), v2, value);
+  for (int j = 3; j < cnt; ++j) value = __fmaf_rn(resample_frac(t, j), __ldg(p + j), value);
+  out[(long long)z * go.ps + (long long)y * go.ld + x] = __fmul_rn(t.norm, value);
+}
+
 int launch_resample_axis(const float* in, Dims gin, float* out, Dims gout, int axis, ZRange zr,
                          cudaStream_t st) {
   if (zr.end <= zr.begin) return FLOW3D_OK;
   dim3 block(32, 8, 1);
   dim3 grid((gout.w + 31) / 32, (gout.h + 7) / 8, zr.end - zr.begin);
-  if (axis == 0) resample_axis_kernel<0><<<grid, block, 0, st>>>(in, gin, out, gout, zr.begin);
+  static const bool scalar_only = [] { const char* e = getenv("FLOW3D_RESAMPLE_SCALAR"); return e && *e == '1'; }();
+  const bool vec_ok = !scalar_only && (gin.ld % 4 == 0) && (gout.ld % 4 == 0) && (gin.ps % 4 == 0) && (gout.ps % 4 == 0) &&
+                      aligned16(in) && aligned16(out);
+  if (axis != 0 && vec_ok) {
+    dim3 g4((gout.w + 127) / 128, (gout.h + 7) / 8, zr.end - zr.begin);
+    if (axis == 1) resample_axis_vec4_kernel<1><<<g4, block, 0, st>>>(in, gin, out, gout, zr.begin);
+    else resample_axis_vec4_kernel<2><<<g4, block, 0, st>>>(in, gin, out, gout, zr.begin);
+  } else if (axis == 0 && !scalar_only) resample_x_kernel<<<grid, block, 0, st>>>(in, gin, out, gout, zr.begin);
+  else if (axis == 0) resample_axis_kernel<0><<<grid, block, 0, st>>>(in, gin, out, gout, zr.begin);
   else if (axis == 1) resample_axis_kernel<1><<<grid, block, 0, st>>>(in, gin, out, gout, zr.begin);
   else resample_axis_kernel<2><<<grid, block, 0, st>>>(in, gin, out, gout, zr.begin);
   count_launch();

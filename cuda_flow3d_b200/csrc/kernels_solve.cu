@@ -102,6 +102,8 @@ struct SweepArgs {
   int lpr;     // lanes per row segment (32, 16 or 8)
   int pf1;     // L1 prefetch of the next plane (0 = off)
   int wx;      // warps side by side along x within a block
+  float* oksi; // KSI variant: the data-term weight is computed here (not read from `ksi`) and stored
+  float eps_d;
 };
 
 // Lane layout: a warp covers 32/lpr consecutive rows x (lpr*VEC) columns (lpr = lanes per row, a power
@@ -173,6 +175,7 @@ template <int VEC>
 struct PlaneRegs {
   Vec<VEC> Su, Sv, Sw, ph;  // live while the plane is next / current / previous
   Vec<VEC> u, v, w, dv, dw; // live while the plane is next / current
+  Vec<VEC> du;              // KSI variant only (dead code otherwise)
 };
 
 template <int VEC>
@@ -188,11 +191,11 @@ __device__ __forceinline__ void load_plane(const SweepArgs& a, unsigned o, Plane
   r.u = ldv<VEC>(a.u + o);
   r.v = ldv<VEC>(a.v + o);
   r.w = ldv<VEC>(a.w + o);
-  const Vec<VEC> du = ldv<VEC>(a.du + o);
+  r.du = ldv<VEC>(a.du + o);
   r.dv = ldv<VEC>(a.dv + o);
   r.dw = ldv<VEC>(a.dw + o);
   r.ph = ldv<VEC>(a.phi + o);
-  r.Su = addv<VEC>(r.u, du);
+  r.Su = addv<VEC>(r.u, r.du);
   r.Sv = addv<VEC>(r.v, r.dv);
   r.Sw = addv<VEC>(r.w, r.dw);
 }
@@ -213,7 +216,7 @@ __device__ __forceinline__ void x_neighbours_interior(const Vec<VEC>& c, float h
 }
 
 // one plane of the sweep: P = previous plane, C = current, N = receives plane z+1
-template <int VEC, bool EDGE>
+template <int VEC, bool EDGE, bool KSI>
 __device__ __forceinline__ void sweep_plane(const SweepArgs& a, const Dims& g, const SweepCtx<VEC>& c, int z,
                                             const PlaneRegs<VEC>& P, const PlaneRegs<VEC>& C, PlaneRegs<VEC>& N) {
   const unsigned ps = c.ps;
@@ -230,7 +233,8 @@ __device__ __forceinline__ void sweep_plane(const SweepArgs& a, const Dims& g, c
     if (zp0 < g.d) {
       const unsigned o = (unsigned)zp0 * ps + c.row_c;
       prefetch_l2(a.fx + o); prefetch_l2(a.fy + o); prefetch_l2(a.fz + o);
-      prefetch_l2(a.ft + o); prefetch_l2(a.ksi + o);
+      prefetch_l2(a.ft + o);
+      if constexpr (!KSI) prefetch_l2(a.ksi + o);
     }
   }
   // ---- next plane (reflect at the rear face) --------------------------------------------------
@@ -241,7 +245,8 @@ __device__ __forceinline__ void sweep_plane(const SweepArgs& a, const Dims& g, c
   const Vec<VEC> fy = ldv<VEC>(a.fy + oc);
   const Vec<VEC> fz = ldv<VEC>(a.fz + oc);
   const Vec<VEC> ft = ldv<VEC>(a.ft + oc);
-  const Vec<VEC> ks = ldv<VEC>(a.ksi + oc);
+  Vec<VEC> ks;
+  if constexpr (!KSI) ks = ldv<VEC>(a.ksi + oc);
   // ---- y neighbours of the current plane -------------------------------------------------------
   const unsigned om = pl + c.row_m;
   const unsigned op = pl + c.row_p;
@@ -326,6 +331,21 @@ __device__ __forceinline__ void sweep_plane(const SweepArgs& a, const Dims& g, c
     sumW = __fmaf_rn(azm, __fsub_rn(P.Sw.v[i], wc), sumW);
     // solve_3d.cu:492-502; numerators as the reference's SASS evaluates them (ptxas contracts the
     // PTX's mul+sub pairs): n = fma(-J13, dw, fma(-J12, dv, -J14))
+    if constexpr (KSI) {
+      // data-term weight of this outer iteration, from the iterate the iteration starts with: the
+      // xi half of compute_phi_ksi_3d (solve_3d.cu:250-260), operation for operation as in
+      // phi_ksi_kernel below; stored for the remaining sweeps of the iteration
+      const float gt = ft.v[i];
+      const float du = C.du.v[i], dv = C.dv.v[i], dw = C.dw.v[i];
+      const float r1 = __fadd_rn(J14, __fmaf_rn(J13, dw, __fmaf_rn(J11, du, __fmul_rn(J12, dv))));
+      const float r2 = __fadd_rn(J24, __fmaf_rn(J23, dw, __fmaf_rn(J12, du, __fmul_rn(J22, dv))));
+      const float r3 = __fadd_rn(J34, __fmaf_rn(J33, dw, __fmaf_rn(J23, dv, __fmul_rn(J13, du))));
+      const float r4 = __fmaf_rn(gt, gt, __fmaf_rn(J34, dw, __fmaf_rn(J14, du, __fmul_rn(J24, dv))));
+      float sv = __fadd_rn(__fmaf_rn(dw, r3, __fmaf_rn(du, r1, __fmul_rn(dv, r2))), r4);
+      sv = __fmul_rn(sv, (sv > 0.f) ? 1.f : 0.f);
+      const float sq2 = __fsqrt_rn(__fmaf_rn(a.eps_d, a.eps_d, sv));
+      ks.v[i] = __frcp_rn(__fadd_rn(sq2, sq2));
+    }
     const float k = ks.v[i];
     const float ndu = __fmaf_rn(-J13, C.dw.v[i], __fmaf_rn(-J12, C.dv.v[i], -J14));
     const float r_du = __fdiv_rn(__fmaf_rn(k, ndu, sumU), __fmaf_rn(J11, k, sumH));
@@ -341,10 +361,11 @@ __device__ __forceinline__ void sweep_plane(const SweepArgs& a, const Dims& g, c
     stv<VEC>(a.odu + oc, rdu);
     stv<VEC>(a.odv + oc, rdv);
     stv<VEC>(a.odw + oc, rdw);
+    if constexpr (KSI) stv<VEC>(a.oksi + oc, ks);
   }
 }
 
-template <int VEC, bool EDGE>
+template <int VEC, bool EDGE, bool KSI>
 __device__ __forceinline__ void sweep_march(const SweepArgs& a, const Dims& g, const SweepCtx<VEC>& c, int z_begin,
                                             int z_end) {
   PlaneRegs<VEC> A, B, Cc;
@@ -352,16 +373,16 @@ __device__ __forceinline__ void sweep_march(const SweepArgs& a, const Dims& g, c
   load_plane<VEC>(a, (unsigned)z_neighbour(g, z_begin, -1) * c.ps + c.row_c, A);
   load_plane<VEC>(a, (unsigned)z_begin * c.ps + c.row_c, B);
   for (int z = z_begin; z < z_end; z += 3) {
-    sweep_plane<VEC, EDGE>(a, g, c, z, A, B, Cc);
+    sweep_plane<VEC, EDGE, KSI>(a, g, c, z, A, B, Cc);
     if (z + 1 >= z_end) break;
-    sweep_plane<VEC, EDGE>(a, g, c, z + 1, B, Cc, A);
+    sweep_plane<VEC, EDGE, KSI>(a, g, c, z + 1, B, Cc, A);
     if (z + 2 >= z_end) break;
-    sweep_plane<VEC, EDGE>(a, g, c, z + 2, Cc, A, B);
+    sweep_plane<VEC, EDGE, KSI>(a, g, c, z + 2, Cc, A, B);
   }
 }
 
 // single-body loop: the roles rotate by copying (the compiler turns most copies into renames)
-template <int VEC, bool EDGE>
+template <int VEC, bool EDGE, bool KSI>
 __device__ __forceinline__ void sweep_march1(const SweepArgs& a, const Dims& g, const SweepCtx<VEC>& c, int z_begin,
                                              int z_end) {
   PlaneRegs<VEC> P, C, N;
@@ -369,13 +390,13 @@ __device__ __forceinline__ void sweep_march1(const SweepArgs& a, const Dims& g, 
   load_plane<VEC>(a, (unsigned)z_begin * c.ps + c.row_c, C);
 #pragma unroll 1
   for (int z = z_begin; z < z_end; ++z) {
-    sweep_plane<VEC, EDGE>(a, g, c, z, P, C, N);
+    sweep_plane<VEC, EDGE, KSI>(a, g, c, z, P, C, N);
     P.Su = C.Su; P.Sv = C.Sv; P.Sw = C.Sw; P.ph = C.ph;
     C = N;
   }
 }
 
-template <int VEC, int MINB, int ROT, int SPEC>
+template <int VEC, int MINB, int ROT, int SPEC, bool KSI = false>
 __global__ void __launch_bounds__(128, MINB) sweep_kernel(const SweepArgs a) {
   const Dims g = a.g;
   const LaneMap lm = lane_map<VEC>(a.lpr, g.w, g.h, a.wx);
@@ -414,11 +435,11 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const SweepArgs a) {
   const int tx0 = lm.tile_x * a.lpr * VEC, tx1 = tx0 + a.lpr * VEC;
   const bool edge = (tx0 == 0) || (tx1 > g.w - 1);  // warp-uniform
   if constexpr (ROT) {
-    if (edge || !SPEC) sweep_march<VEC, true>(a, g, c, z_begin, z_end);
-    else sweep_march<VEC, false>(a, g, c, z_begin, z_end);
+    if (edge || !SPEC) sweep_march<VEC, true, KSI>(a, g, c, z_begin, z_end);
+    else sweep_march<VEC, false, KSI>(a, g, c, z_begin, z_end);
   } else {
-    if (edge || !SPEC) sweep_march1<VEC, true>(a, g, c, z_begin, z_end);
-    else sweep_march1<VEC, false>(a, g, c, z_begin, z_end);
+    if (edge || !SPEC) sweep_march1<VEC, true, KSI>(a, g, c, z_begin, z_end);
+    else sweep_march1<VEC, false, KSI>(a, g, c, z_begin, z_end);
   }
 }
 
@@ -595,6 +616,13 @@ static int launch_sweep_cfg(SweepArgs a, const Dims& g, ZRange zr, TuneCfg cfg, 
   pick_grid(g, zr, vec, a.lpr, rows, grid, block, a.zchunk, a.wx, vec == 4 ? 2 : 4,
             cfg.nchunks > 0 ? chunk_len(zr.end - zr.begin, cfg.nchunks) : 0);
   static const int rot = env_int("FLOW3D_SWEEP_ROT", 0), spec = env_int("FLOW3D_SWEEP_SPEC", 0);
+  if (a.oksi) {  // first sweep of an outer iteration: computes and stores ksi
+    if (vec == 4) sweep_kernel<4, 2, 0, 0, true><<<grid, block, 0, st>>>(a);
+    else if (vec == 2) sweep_kernel<2, 4, 0, 0, true><<<grid, block, 0, st>>>(a);
+    else sweep_kernel<1, 4, 0, 0, true><<<grid, block, 0, st>>>(a);
+    count_launch();
+    return check_launch("sweep_kernel<KSI>");
+  }
   if (vec == 4) {
     if (rot && spec) sweep_kernel<4, 2, 1, 1><<<grid, block, 0, st>>>(a);
     else if (rot) sweep_kernel<4, 2, 1, 0><<<grid, block, 0, st>>>(a);
@@ -612,15 +640,16 @@ static int launch_sweep_cfg(SweepArgs a, const Dims& g, ZRange zr, TuneCfg cfg, 
 int launch_sweep(const float* fx, const float* fy, const float* fz, const float* ft,
                  const float* u, const float* v, const float* w, const float* du, const float* dv,
                  const float* dw, const float* phi, const float* ksi, Dims g, ZRange zr, float hx,
-                 float hy, float hz, float alpha, float* odu, float* odv, float* odw, cudaStream_t st) {
+                 float hy, float hz, float alpha, float* odu, float* odv, float* odw, cudaStream_t st,
+                 float* ksi_out, float eps_d) {
   if (zr.end <= zr.begin) return FLOW3D_OK;
   SweepArgs a{fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, odu, odv, odw, g, hx, hy, hz, alpha, 0, 0,
-              zr.begin, zr.end, 32, 0, 1};
+              zr.begin, zr.end, 32, 0, 1, ksi_out, eps_d};
   const int nz = zr.end - zr.begin;
   TuneCfg cfg{pick_vec(g), 0};
   static const int forced_vec = env_int("FLOW3D_SWEEP_VEC", 0);
   if (autotune_enabled() && forced_vec == 0 && nz >= 8 && (long long)g.w * g.h * nz >= 32768) {
-    const TuneKey key = tune_key(0, g, zr);
+    const TuneKey key = tune_key(ksi_out ? 2 : 0, g, zr);
     bool have;
     {
       std::lock_guard<std::mutex> lk(g_tune_mu);
@@ -677,7 +706,9 @@ __device__ __forceinline__ float cnum(float fp, float fm, float dfp, float dfm) 
 // Same structure as the sweep: one warp per row segment of 32*VEC voxels marching along z, the six
 // stencil fields (u,du,v,dv,w,dw) register-rotated in z, x neighbours by shuffle, y neighbours from
 // the adjacent rows through L1.
-template <int VEC>
+// WITH_KSI = false: phi only (the solver computes ksi in the first sweep of the outer iteration, which
+// holds every operand of it anyway; see sweep_plane<.., KSI>)
+template <int VEC, bool WITH_KSI = true>
 __global__ void __launch_bounds__(128) phi_ksi_kernel(const PhiKsiArgs a, int zchunk, int pf, int zs, int ze,
                                                       int lpr) {
   const Dims g = a.g;
@@ -720,10 +751,12 @@ __global__ void __launch_bounds__(128) phi_ksi_kernel(const PhiKsiArgs a, int zc
 #pragma unroll
         for (int f = 0; f < 6; ++f) prefetch_l2(F[f] + o);
       }
-      const int zp0 = z + pf;
-      if (zp0 < g.d) {
-        const unsigned o = (unsigned)zp0 * ps + row_c;
-        prefetch_l2(a.fx + o); prefetch_l2(a.fy + o); prefetch_l2(a.fz + o); prefetch_l2(a.ft + o);
+      if constexpr (WITH_KSI) {
+        const int zp0 = z + pf;
+        if (zp0 < g.d) {
+          const unsigned o = (unsigned)zp0 * ps + row_c;
+          prefetch_l2(a.fx + o); prefetch_l2(a.fy + o); prefetch_l2(a.fz + o); prefetch_l2(a.ft + o);
+        }
       }
     }
     const unsigned on = (unsigned)z_neighbour(g, z, 1) * ps + row_c;
@@ -735,8 +768,10 @@ __global__ void __launch_bounds__(128) phi_ksi_kernel(const PhiKsiArgs a, int zc
       ym[f] = ldv<VEC>(F[f] + om);
       yp[f] = ldv<VEC>(F[f] + op);
     }
-    const Vec<VEC> fx = ldv<VEC>(a.fx + oc), fy = ldv<VEC>(a.fy + oc), fz = ldv<VEC>(a.fz + oc),
-                   ft = ldv<VEC>(a.ft + oc);
+    Vec<VEC> fx, fy, fz, ft;
+    if constexpr (WITH_KSI) {
+      fx = ldv<VEC>(a.fx + oc); fy = ldv<VEC>(a.fy + oc); fz = ldv<VEC>(a.fz + oc); ft = ldv<VEC>(a.ft + oc);
+    }
     float halo[6];
     {
       const unsigned oh = pl + row_h;
@@ -790,25 +825,26 @@ __global__ void __launch_bounds__(128) phi_ksi_kernel(const PhiKsiArgs a, int zc
       acc = __fmaf_rn(a.eps_s, a.eps_s, acc);
       const float sq = __fsqrt_rn(acc);
       ophi.v[i] = __frcp_rn(__fadd_rn(sq, sq));
-
-      const float gx = fx.v[i], gy = fy.v[i], gz = fz.v[i], gt = ft.v[i];
-      const float J11 = __fmul_rn(gx, gx), J22 = __fmul_rn(gy, gy), J33 = __fmul_rn(gz, gz);
-      const float J12 = __fmul_rn(gx, gy), J13 = __fmul_rn(gx, gz), J23 = __fmul_rn(gy, gz);
-      const float J14 = __fmul_rn(gx, gt), J24 = __fmul_rn(gy, gt), J34 = __fmul_rn(gz, gt);
-      const float du = cur[1].v[i], dv = cur[3].v[i], dw = cur[5].v[i];
-      // solve_3d.cu:250-254, operation by operation (row 3 keeps J13*du as the rounded product)
-      const float r1 = __fadd_rn(J14, __fmaf_rn(J13, dw, __fmaf_rn(J11, du, __fmul_rn(J12, dv))));
-      const float r2 = __fadd_rn(J24, __fmaf_rn(J23, dw, __fmaf_rn(J12, du, __fmul_rn(J22, dv))));
-      const float r3 = __fadd_rn(J34, __fmaf_rn(J33, dw, __fmaf_rn(J23, dv, __fmul_rn(J13, du))));
-      const float r4 = __fmaf_rn(gt, gt, __fmaf_rn(J34, dw, __fmaf_rn(J14, du, __fmul_rn(J24, dv))));
-      float sv = __fadd_rn(__fmaf_rn(dw, r3, __fmaf_rn(du, r1, __fmul_rn(dv, r2))), r4);
-      sv = __fmul_rn(sv, (sv > 0.f) ? 1.f : 0.f);
-      const float sq2 = __fsqrt_rn(__fmaf_rn(a.eps_d, a.eps_d, sv));
-      oksi.v[i] = __frcp_rn(__fadd_rn(sq2, sq2));
+      if constexpr (WITH_KSI) {
+        const float gx = fx.v[i], gy = fy.v[i], gz = fz.v[i], gt = ft.v[i];
+        const float J11 = __fmul_rn(gx, gx), J22 = __fmul_rn(gy, gy), J33 = __fmul_rn(gz, gz);
+        const float J12 = __fmul_rn(gx, gy), J13 = __fmul_rn(gx, gz), J23 = __fmul_rn(gy, gz);
+        const float J14 = __fmul_rn(gx, gt), J24 = __fmul_rn(gy, gt), J34 = __fmul_rn(gz, gt);
+        const float du = cur[1].v[i], dv = cur[3].v[i], dw = cur[5].v[i];
+        // solve_3d.cu:250-254, operation by operation (row 3 keeps J13*du as the rounded product)
+        const float r1 = __fadd_rn(J14, __fmaf_rn(J13, dw, __fmaf_rn(J11, du, __fmul_rn(J12, dv))));
+        const float r2 = __fadd_rn(J24, __fmaf_rn(J23, dw, __fmaf_rn(J12, du, __fmul_rn(J22, dv))));
+        const float r3 = __fadd_rn(J34, __fmaf_rn(J33, dw, __fmaf_rn(J23, dv, __fmul_rn(J13, du))));
+        const float r4 = __fmaf_rn(gt, gt, __fmaf_rn(J34, dw, __fmaf_rn(J14, du, __fmul_rn(J24, dv))));
+        float sv = __fadd_rn(__fmaf_rn(dw, r3, __fmaf_rn(du, r1, __fmul_rn(dv, r2))), r4);
+        sv = __fmul_rn(sv, (sv > 0.f) ? 1.f : 0.f);
+        const float sq2 = __fsqrt_rn(__fmaf_rn(a.eps_d, a.eps_d, sv));
+        oksi.v[i] = __frcp_rn(__fadd_rn(sq2, sq2));
+      }
     }
     if (active) {
       stv<VEC>(a.phi + oc, ophi);
-      stv<VEC>(a.ksi + oc, oksi);
+      if constexpr (WITH_KSI) stv<VEC>(a.ksi + oc, oksi);
     }
 #pragma unroll
     for (int f = 0; f < 6; ++f) {
@@ -826,7 +862,11 @@ static int launch_phi_ksi_cfg(const PhiKsiArgs& a, const Dims& g, ZRange zr, Tun
   static const int forced_lpr = env_int("FLOW3D_LPR", 0);
   const int lpr = (forced_lpr == 8 || forced_lpr == 16 || forced_lpr == 32) ? forced_lpr : pick_lpr(g.w, vec);
   pick_grid(g, zr, vec, lpr, 4, grid, block, zchunk, 1, 5, cfg.nchunks > 0 ? chunk_len(zr.end - zr.begin, cfg.nchunks) : 0);
-  if (vec == 4) phi_ksi_kernel<4><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end, lpr);
+  if (!a.ksi) {
+    if (vec == 4) phi_ksi_kernel<4, false><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end, lpr);
+    else if (vec == 2) phi_ksi_kernel<2, false><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end, lpr);
+    else phi_ksi_kernel<1, false><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end, lpr);
+  } else if (vec == 4) phi_ksi_kernel<4><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end, lpr);
   else if (vec == 2) phi_ksi_kernel<2><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end, lpr);
   else phi_ksi_kernel<1><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end, lpr);
   count_launch();
@@ -845,7 +885,7 @@ int launch_phi_ksi(const float* fx, const float* fy, const float* fz, const floa
   TuneCfg cfg{vec, 0};
   const int nz = zr.end - zr.begin;
   if (autotune_enabled() && forced == 0 && nz >= 8 && (long long)g.w * g.h * nz >= 32768) {
-    const TuneKey key = tune_key(1, g, zr);
+    const TuneKey key = tune_key(ksi ? 1 : 3, g, zr);
     bool have;
     {
       std::lock_guard<std::mutex> lk(g_tune_mu);
@@ -856,10 +896,15 @@ int launch_phi_ksi(const float* fx, const float* fy, const float* fz, const floa
     if (!have) {
       std::vector<TuneCfg> cands;
       std::vector<int> chunks;
-      const int lpr = pick_lpr(g.w, vec);
-      const long long per_plane = (long long)((g.w + lpr * vec - 1) / (lpr * vec)) * ((g.h + 4 * (32 / lpr) - 1) / (4 * (32 / lpr)));
-      chunk_candidates(nz, per_plane, chunks);
-      for (int c : chunks) cands.push_back(TuneCfg{vec, c});
+      int vecs[2] = {vec, (vec == 2 && g.w >= 128) ? 4 : 0};
+      for (int vi = 0; vi < 2; ++vi) {
+        const int vc = vecs[vi];
+        if (!vc) continue;
+        const int lpr = pick_lpr(g.w, vc);
+        const long long per_plane = (long long)((g.w + lpr * vc - 1) / (lpr * vc)) * ((g.h + 4 * (32 / lpr) - 1) / (4 * (32 / lpr)));
+        chunk_candidates(nz, per_plane, chunks);
+        for (int c : chunks) cands.push_back(TuneCfg{vc, c});
+      }
       F3D_TRY_RC(tune_pick(cands, [&](TuneCfg c) { return launch_phi_ksi_cfg(a, g, zr, c, st); }, st, &cfg));
       std::lock_guard<std::mutex> lk(g_tune_mu);
       g_tune[key] = cfg;
