@@ -40,6 +40,9 @@ def parse():
     ap.add_argument("--size", type=int, default=0, help="cube edge (default 512)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--levels", type=int, default=0,
+                    help="profiling aid: run only the finest LEVELS pyramid levels (NOT the benchmark workload; the "
+                         "JSON line says so)")
     ap.add_argument("--replicas", action="store_true", help="N>1: independent 512^3 replicas instead of one sharded solve")
     return ap.parse_args()
 
@@ -338,6 +341,8 @@ def run_ours(args, rank, world, local_rank):
     n = args.size or 512
     W = H = D = n
     P = dict(pkg.DEFAULTS)
+    if args.levels > 0:
+        P["warp_levels_count"] = args.levels
     params = pkg.api.make_params(P)
     ld = int(L.flow3d_aligned_ld(W))
     vol = ld * H * D
@@ -479,6 +484,7 @@ def run_ours(args, rank, world, local_rank):
             "data": "synthetic",
             "config": {"workload": "synthetic %d^3 pair with known rigid motion (BASELINE configs[2]), default "
                                    "parameters: %d levels x 40 outer x 5 inner sweeps, median 5, sigma 2" % (n, nlev),
+                       "reduced_levels_profiling_run": args.levels if args.levels > 0 else None,
                        "parallelism": "1 GPU" if world == 1 else "%d independent replicas (one volume pair per GPU)" % world,
                        "inputs_larger_than_l2": bool(vol * 4 > 126e6), "level_voxels": nsum,
                        "parity": "bit-identical to the reference CUDA build (tests/)"},

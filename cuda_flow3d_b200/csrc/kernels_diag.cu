@@ -36,8 +36,10 @@ __global__ void __launch_bounds__(256) update_norm_kernel(const float* __restric
       const float d1 = __fsub_rn(__ldg(a1 + o + x), __ldg(b1 + o + x));
       const float d2 = __fsub_rn(__ldg(a2 + o + x), __ldg(b2 + o + x));
       sum += (double)d0 * (double)d0 + (double)d1 * (double)d1 + (double)d2 * (double)d2;
-      const float m = fmaxf(fabsf(d0), fmaxf(fabsf(d1), fabsf(d2)));
-      mx = (m > mx || m != m) ? m : mx;  // NaN sticks
+      const float m0 = fabsf(d0), m1 = fabsf(d1), m2 = fabsf(d2);
+      mx = (m0 > mx || m0 != m0) ? m0 : mx;  // NaN sticks (fmaxf would drop it)
+      mx = (m1 > mx || m1 != m1) ? m1 : mx;
+      mx = (m2 > mx || m2 != m2) ? m2 : mx;
     }
   }
 #pragma unroll

@@ -708,12 +708,12 @@ __device__ __forceinline__ float cnum(float fp, float fm, float dfp, float dfm) 
 // the adjacent rows through L1.
 // WITH_KSI = false: phi only (the solver computes ksi in the first sweep of the outer iteration, which
 // holds every operand of it anyway; see sweep_plane<.., KSI>)
-template <int VEC, bool WITH_KSI = true>
-__global__ void __launch_bounds__(128) phi_ksi_kernel(const PhiKsiArgs a, int zchunk, int pf, int zs, int ze,
-                                                      int lpr) {
+// EDGE: the warp's tile touches an x face of the volume (mirror selects needed); interior warps run a
+// copy of the body without them
+template <int VEC, bool WITH_KSI, bool EDGE>
+__device__ __forceinline__ void phi_ksi_body(const PhiKsiArgs& a, const LaneMap& lm, int zchunk, int pf, int zs,
+                                             int ze) {
   const Dims g = a.g;
-  const LaneMap lm = lane_map<VEC>(lpr, g.w, g.h);
-  if (lm.first_row >= g.h) return;
   const int y = lm.y;
   const bool active = lm.active;
   const int x0 = lm.x0;
@@ -726,7 +726,7 @@ __global__ void __launch_bounds__(128) phi_ksi_kernel(const PhiKsiArgs a, int zc
   const unsigned row_m = (unsigned)mirror_idx(y - 1, g.h) * g.ld + x0;
   const unsigned row_p = (unsigned)mirror_idx(y + 1, g.h) * g.ld + x0;
   const unsigned row_h = (unsigned)y * g.ld + xh;
-  // divisors 2h are loop invariants: exact division through the double reciprocal (common.cuh)
+  // divisors 2h are loop invariants: exact division through the FMA sequence of common.cuh
   const ConstDiv thx = make_const_div(__fadd_rn(a.hx, a.hx)), thy = make_const_div(__fadd_rn(a.hy, a.hy)),
                  thz = make_const_div(__fadd_rn(a.hz, a.hz));
   const bool fast_div = thx.fast && thy.fast && thz.fast;
@@ -779,7 +779,10 @@ __global__ void __launch_bounds__(128) phi_ksi_kernel(const PhiKsiArgs a, int zc
       for (int f = 0; f < 6; ++f) halo[f] = __ldg(F[f] + oh);
     }
 #pragma unroll
-    for (int f = 0; f < 6; ++f) x_neighbours<VEC>(cur[f], halo[f], lm.left_edge, lm.right_edge, x0, g.w, xm[f], xp[f]);
+    for (int f = 0; f < 6; ++f) {
+      if constexpr (EDGE) x_neighbours<VEC>(cur[f], halo[f], lm.left_edge, lm.right_edge, x0, g.w, xm[f], xp[f]);
+      else x_neighbours_interior<VEC>(cur[f], halo[f], lm.left_edge, lm.right_edge, xm[f], xp[f]);
+    }
 
     Vec<VEC> ophi, oksi;
 #pragma unroll
@@ -795,34 +798,32 @@ __global__ void __launch_bounds__(128) phi_ksi_kernel(const PhiKsiArgs a, int zc
       nm[6] = cnum(xp[4].v[i], xm[4].v[i], xp[5].v[i], xm[5].v[i]);
       nm[7] = cnum(yp[4].v[i], ym[4].v[i], yp[5].v[i], ym[5].v[i]);
       nm[8] = cnum(next[4].v[i], prev[4].v[i], next[5].v[i], prev[5].v[i]);
-      // quotients by the loop-invariant 2h through the FMA sequence (common.cuh).  One range test for
-      // the nine: the largest |numerator| bit pattern (NaN / Inf are the largest of all) must stay below
-      // 2^100.  Tiny numerators need no test here: a quotient below 2^-80 only ever enters the sum of
-      // squares below, where its square is an exact zero whichever way it was rounded.
-      unsigned big = 0u;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) big = max(big, __float_as_uint(nm[k]) & 0x7fffffffu);
+      // Quotients by the loop-invariant 2h through the FMA sequence (common.cuh), with no range test up
+      // front: the sequence is exact for |numerator| <= 2^100, and a numerator beyond that (or Inf / NaN)
+      // makes the sum of squares below Inf or NaN, which is what triggers the IEEE-division path.  Tiny
+      // numerators need no test: a quotient below 2^-80 only enters the sum as an exact zero square.
+      // Sum: solve_3d.cu:217-218 as contracted by nvcc, mul(duy,duy) first, then one fma per term.
+      auto sum_sq = [&](const float (&q)[9]) {
+        float acc = __fmul_rn(q[1], q[1]);
+        acc = __fmaf_rn(q[0], q[0], acc);
+        acc = __fmaf_rn(q[2], q[2], acc);
+        acc = __fmaf_rn(q[3], q[3], acc);
+        acc = __fmaf_rn(q[4], q[4], acc);
+        acc = __fmaf_rn(q[5], q[5], acc);
+        acc = __fmaf_rn(q[6], q[6], acc);
+        acc = __fmaf_rn(q[7], q[7], acc);
+        acc = __fmaf_rn(q[8], q[8], acc);
+        return __fmaf_rn(a.eps_s, a.eps_s, acc);
+      };
       float q[9];
-      if (fast_div && big <= 0x71800000u) {  // 2^100
 #pragma unroll
-        for (int k = 0; k < 9; ++k) q[k] = div_const_unchecked(nm[k], (k % 3 == 0) ? thx : (k % 3 == 1) ? thy : thz);
-      } else {
+      for (int k = 0; k < 9; ++k) q[k] = div_const_unchecked(nm[k], (k % 3 == 0) ? thx : (k % 3 == 1) ? thy : thz);
+      float acc = sum_sq(q);
+      if (!(fast_div && acc <= 3.0e38f)) {
 #pragma unroll
         for (int k = 0; k < 9; ++k) q[k] = __fdiv_rn(nm[k], (k % 3 == 0) ? thx.c : (k % 3 == 1) ? thy.c : thz.c);
+        acc = sum_sq(q);
       }
-      const float dux = q[0], duy = q[1], duz = q[2], dvx = q[3], dvy = q[4], dvz = q[5], dwx = q[6], dwy = q[7],
-                  dwz = q[8];
-      // solve_3d.cu:217-218 as contracted by nvcc: mul(duy,duy) first, then one fma per term
-      float acc = __fmul_rn(duy, duy);
-      acc = __fmaf_rn(dux, dux, acc);
-      acc = __fmaf_rn(duz, duz, acc);
-      acc = __fmaf_rn(dvx, dvx, acc);
-      acc = __fmaf_rn(dvy, dvy, acc);
-      acc = __fmaf_rn(dvz, dvz, acc);
-      acc = __fmaf_rn(dwx, dwx, acc);
-      acc = __fmaf_rn(dwy, dwy, acc);
-      acc = __fmaf_rn(dwz, dwz, acc);
-      acc = __fmaf_rn(a.eps_s, a.eps_s, acc);
       const float sq = __fsqrt_rn(acc);
       ophi.v[i] = __frcp_rn(__fadd_rn(sq, sq));
       if constexpr (WITH_KSI) {
@@ -852,6 +853,17 @@ __global__ void __launch_bounds__(128) phi_ksi_kernel(const PhiKsiArgs a, int zc
       cur[f] = next[f];
     }
   }
+}
+
+template <int VEC, bool WITH_KSI = true>
+__global__ void __launch_bounds__(128) phi_ksi_kernel(const PhiKsiArgs a, int zchunk, int pf, int zs, int ze,
+                                                      int lpr) {
+  const LaneMap lm = lane_map<VEC>(lpr, a.g.w, a.g.h);
+  if (lm.first_row >= a.g.h) return;
+  const int tx0 = lm.tile_x * lpr * VEC, tx1 = tx0 + lpr * VEC;
+  const bool edge = (tx0 == 0) || (tx1 > a.g.w - 1);  // warp-uniform
+  if (edge) phi_ksi_body<VEC, WITH_KSI, true>(a, lm, zchunk, pf, zs, ze);
+  else phi_ksi_body<VEC, WITH_KSI, false>(a, lm, zchunk, pf, zs, ze);
 }
 
 static int launch_phi_ksi_cfg(const PhiKsiArgs& a, const Dims& g, ZRange zr, TuneCfg cfg, cudaStream_t st) {

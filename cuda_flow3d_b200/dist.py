@@ -306,6 +306,78 @@ class OracleBackend:
 
 
 # =====================================================================================================
+class TorchComm:
+    """the three communication patterns of the sharded solve on torch.distributed (NCCL on GPUs, gloo in
+    the CPU tests): neighbour send/recv, one scalar max, one all-gather of equal-sized pieces"""
+
+    def __init__(self, rank=None, world=None):
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+
+    def sendrecv(self, ops):
+        """ops: list of ("send" | "recv", tensor, peer), matched in order per peer"""
+        p2p = [dist.P2POp(dist.isend if kind == "send" else dist.irecv, t, peer) for kind, t, peer in ops]
+        for r in dist.batch_isend_irecv(p2p):
+            r.wait()
+
+    def allreduce_max(self, value, device):
+        t = torch.tensor([value], dtype=torch.float32, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_gather(self, piece):
+        pieces = [torch.empty_like(piece) for _ in range(self.world)]
+        dist.all_gather(pieces, piece)
+        return pieces
+
+
+class LocalComm:
+    """the same patterns between `world` threads of ONE process (the out-of-core solver's virtual ranks):
+    per-pair FIFO mailboxes for send/recv, a barrier for the two collectives"""
+
+    class Shared:
+        def __init__(self, world):
+            import queue
+            import threading
+            self.world = world
+            self.box = {(s, d): queue.Queue() for s in range(world) for d in range(world)}
+            self.barrier = threading.Barrier(world)
+            self.slots = [None] * world
+            self.failed = threading.Event()  # set by a rank that died: the others stop waiting for it
+
+    def __init__(self, shared, rank):
+        self.sh, self.rank, self.world = shared, rank, shared.world
+
+    def sendrecv(self, ops):
+        for kind, t, peer in ops:  # post every send first: nobody blocks on a full mailbox
+            if kind == "send":
+                self.sh.box[(self.rank, peer)].put(t.clone())
+        import queue
+        for kind, t, peer in ops:
+            if kind == "recv":
+                while True:
+                    try:
+                        t.copy_(self.sh.box[(peer, self.rank)].get(timeout=0.5))
+                        break
+                    except queue.Empty:
+                        if self.sh.failed.is_set():
+                            raise RuntimeError("a peer slab failed") from None
+
+    def _exchange_slot(self, value):
+        self.sh.slots[self.rank] = value
+        self.sh.barrier.wait(timeout=600)
+        out = list(self.sh.slots)
+        self.sh.barrier.wait(timeout=600)
+        return out
+
+    def allreduce_max(self, value, device):
+        return float(max(self._exchange_slot(float(value))))
+
+    def all_gather(self, piece):
+        return [p.clone() for p in self._exchange_slot(piece)]
+
+
+# =====================================================================================================
 class ReplicatedFrames:
     """both blurred full-resolution frames live on every rank"""
     global_reach = False
@@ -399,8 +471,7 @@ class ShardedFrames:
             src = Slab(self.slabs[which].planes(s_lo, s_hi), s_lo, D, W)
             out = Slab(piece[:p_hi - p_lo], p_lo, d, w)
             be.resample(src, self.whd, dims, p_lo, p_lo, p_hi, out=out)
-        pieces = [torch.empty_like(piece) for _ in range(world)]
-        dist.all_gather(pieces, piece)
+        pieces = self.s.comm.all_gather(piece)
         full = be.empty(w, hh, d)
         for r in range(world):
             n = bounds[r + 1] - bounds[r]
@@ -415,10 +486,12 @@ class ShardedFlowSolver:
     """Coarse-to-fine solve of OpticalFlowE::ComputeFlow (optical_flow_e.cpp:132-601) with every large
     level sharded along z over the ranks of `group`."""
 
-    def __init__(self, backend, rank=None, world=None, min_planes_per_rank=12, min_voxels_per_rank=1 << 18):
+    def __init__(self, backend, rank=None, world=None, min_planes_per_rank=12, min_voxels_per_rank=1 << 18,
+                 comm=None):
         self.be = backend
-        self.rank = dist.get_rank() if rank is None else rank
-        self.world = dist.get_world_size() if world is None else world
+        self.comm = comm if comm is not None else TorchComm(rank, world)
+        self.rank = self.comm.rank
+        self.world = self.comm.world
         self.min_planes = min_planes_per_rank
         self.min_voxels = min_voxels_per_rank
         self.stats = {"sharded_levels": 0, "replicated_levels": 0, "exchanges": 0, "exchange_bytes": 0}
@@ -452,16 +525,15 @@ class ShardedFlowSolver:
         lo_n, hi_n = self.rank - 1, self.rank + 1
         for t in fields:
             if lo_n >= 0 and a > A:  # my lower ghosts <- rank-1's top planes; rank-1's upper ghosts <- my bottom planes
-                ops.append(dist.P2POp(dist.irecv, t[0:a - A], lo_n))
-                ops.append(dist.P2POp(dist.isend, t[a - A:a - A + min(H, b - a)], lo_n))
+                ops.append(("recv", t[0:a - A], lo_n))
+                ops.append(("send", t[a - A:a - A + min(H, b - a)], lo_n))
             if hi_n < self.world and B > b:
-                ops.append(dist.P2POp(dist.isend, t[b - A - min(H, b - a):b - A], hi_n))
-                ops.append(dist.P2POp(dist.irecv, t[b - A:B - A], hi_n))
+                ops.append(("send", t[b - A - min(H, b - a):b - A], hi_n))
+                ops.append(("recv", t[b - A:B - A], hi_n))
         if ops:
-            for r in dist.batch_isend_irecv(ops):
-                r.wait()
+            self.comm.sendrecv(ops)
             self.stats["exchanges"] += 1
-            self.stats["exchange_bytes"] += sum(op.tensor.numel() * 4 for op in ops if op.op is dist.isend)
+            self.stats["exchange_bytes"] += sum(t.numel() * 4 for kind, t, _ in ops if kind == "send")
 
     def _is_sharded(self, dims, H):
         w, h, d = dims
@@ -545,9 +617,7 @@ class ShardedFlowSolver:
             hz = h[2]
             wmax = be.absmax(flow[2]) if prev is not None else 0.0
             if frames.global_reach and self.world > 1:  # same reach on every rank => same local/gather decision
-                t = torch.tensor([wmax], dtype=torch.float32, device=be.dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                wmax = float(t.item())
+                wmax = self.comm.allreduce_max(wmax, be.dev)
             reach = int(math.ceil(wmax / float(hz))) + 2 if prev is not None else 1
             A1, B1 = max(0, A - reach), min(d, B + reach)
             if frames.global_reach:

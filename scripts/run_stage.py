@@ -20,6 +20,7 @@ ap.add_argument("--size", type=int, default=512)
 ap.add_argument("--dims", type=str, default="")
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--alias-f", action="store_true", help="experiment: pass fx/fy also as fz/ft (13 distinct words)")
+ap.add_argument("--alias-most", action="store_true", help="experiment: one buffer for all nine static fields (7 distinct words)")
 ap.add_argument("--ld-align", type=int, default=0, help="override the row pitch alignment (floats)")
 args = ap.parse_args()
 L = pkg.load()
@@ -58,6 +59,10 @@ o = [torch.empty(n, device="cuda") for _ in range(4)]
 
 def run():
     if args.stage == "sweep":
+        if args.alias_most:
+            check(L.flow3d_sweep(P(phi), P(phi), P(phi), P(phi), P(phi), P(phi), P(phi), P(du), P(dv), P(dw), P(phi), P(phi),
+                                 dims, ld, h, 7.5, P(o[0]), P(o[1]), P(o[2]), sp), "sweep")
+            return 52.0
         if args.alias_f:
             check(L.flow3d_sweep(P(fx), P(fy), P(fx), P(fy), P(u), P(v), P(w), P(du), P(dv), P(dw), P(phi), P(ksi),
                                  dims, ld, h, 7.5, P(o[0]), P(o[1]), P(o[2]), sp), "sweep")
