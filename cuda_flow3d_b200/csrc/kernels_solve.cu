@@ -585,9 +585,15 @@ static int tune_pick(const std::vector<TuneCfg>& cands, Launch&& launch, cudaStr
   cudaEvent_t e0, e1;
   if (cudaEventCreate(&e0) != cudaSuccess) return FLOW3D_ERR_CUDA;
   if (cudaEventCreate(&e1) != cudaSuccess) { cudaEventDestroy(e0); return FLOW3D_ERR_CUDA; }
-  int rc = launch(cands[0]);  // warm
+  // warm-up launch, timed: short kernels get more repetitions per candidate (>= ~1 ms of work each)
+  cudaEventRecord(e0, st);
+  int rc = launch(cands[0]);
+  cudaEventRecord(e1, st);
+  float warm_ms = 1.f;
+  if (cudaEventSynchronize(e1) == cudaSuccess) cudaEventElapsedTime(&warm_ms, e0, e1);
   float best_ms = -1.f;
-  const int reps = 3;
+  int reps = warm_ms > 0.f ? (int)(1.0f / warm_ms + 0.999f) : 3;
+  reps = reps < 3 ? 3 : (reps > 24 ? 24 : reps);
   for (size_t i = 0; i < cands.size() && rc == FLOW3D_OK; ++i) {
     cudaEventRecord(e0, st);
     for (int r = 0; r < reps && rc == FLOW3D_OK; ++r) rc = launch(cands[i]);
