@@ -559,25 +559,29 @@ static inline int chunk_len(int nz, int nchunks) {
   int len = (nz + nchunks - 1) / nchunks;
   return len < 1 ? 1 : len;
 }
-// chunk counts around the static heuristic's choice n0, chunks of at least 4 planes
+// candidate chunk counts: chunk lengths around the static heuristic's choice, plus short chunks (2..8
+// planes) that shorten the dependent z march of small, latency-bound levels
 static void chunk_candidates(int nz, long long per_plane, std::vector<int>& out) {
   const long long want = (long long)sm_count() * 16;
   long long n0 = (want + per_plane - 1) / per_plane;
   if (n0 < 1) n0 = 1;
-  const double f[] = {0.125, 0.25, 0.5, 0.75, 1.0, 1.5, 2.0, 3.0};
+  if (n0 > nz) n0 = nz;
+  const int len0 = chunk_len(nz, (int)n0);
+  int lens[16];
+  int nl = 0;
+  const double f[] = {8.0, 4.0, 2.0, 1.333, 1.0, 0.667, 0.5, 0.333};
+  for (double k : f) lens[nl++] = (int)(len0 * k + 0.5);
+  const int small_lens[] = {2, 3, 4, 6, 8};
+  for (int l : small_lens)
+    if (l < len0) lens[nl++] = l;
   out.clear();
-  int last_len = -1;
-  for (double k : f) {
-    long long n = (long long)(n0 * k + 0.5);
-    if (n < 1) n = 1;
-    int len = chunk_len(nz, (int)(n > nz ? nz : n));
-    if (len < 4) len = nz < 4 ? nz : 4;
+  for (int i = 0; i < nl; ++i) {
+    int len = lens[i] < 2 ? 2 : lens[i];
+    if (len > nz) len = nz;
     const int chunks = (nz + len - 1) / len;
-    if (len == last_len) continue;
     bool dup = false;
     for (int c : out) dup = dup || c == chunks;
     if (!dup) out.push_back(chunks);
-    last_len = len;
   }
 }
 template <class Launch>
@@ -654,7 +658,7 @@ int launch_sweep(const float* fx, const float* fy, const float* fz, const float*
   const int nz = zr.end - zr.begin;
   TuneCfg cfg{pick_vec(g), 0};
   static const int forced_vec = env_int("FLOW3D_SWEEP_VEC", 0);
-  if (autotune_enabled() && forced_vec == 0 && nz >= 8 && (long long)g.w * g.h * nz >= 32768) {
+  if (autotune_enabled() && forced_vec == 0 && nz >= 4) {
     const TuneKey key = tune_key(ksi_out ? 2 : 0, g, zr);
     bool have;
     {
@@ -669,6 +673,7 @@ int launch_sweep(const float* fx, const float* fy, const float* fz, const float*
       int vecs[2] = {cfg.vec, 0};
       if (cfg.vec == 4) vecs[1] = 2;
       else if (cfg.vec == 2 && g.w >= 128) vecs[1] = 4;
+      else if (cfg.vec == 2) vecs[1] = 1;  // narrow levels: more, thinner warps
       for (int vi = 0; vi < 2; ++vi) {
         const int vec = vecs[vi];
         if (!vec) continue;
@@ -902,7 +907,7 @@ int launch_phi_ksi(const float* fx, const float* fy, const float* fz, const floa
   if (forced == 1 || forced == 2 || forced == 4) vec = forced;
   TuneCfg cfg{vec, 0};
   const int nz = zr.end - zr.begin;
-  if (autotune_enabled() && forced == 0 && nz >= 8 && (long long)g.w * g.h * nz >= 32768) {
+  if (autotune_enabled() && forced == 0 && nz >= 4) {
     const TuneKey key = tune_key(ksi ? 1 : 3, g, zr);
     bool have;
     {
