@@ -31,6 +31,25 @@ PHIKSI_BYTES = 40.0    # one phi/ksi voxel update: 8 reads + 2 writes
 SEED = 20240521
 
 
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """Everything libraries print to fd 1 (NCCL's version banner, torchrun notes) goes to stderr; the one
+    JSON line is written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -163,7 +182,7 @@ def run_reference(args, rank, world):
             "config": {"workload": "synthetic %d^3 pair, default parameters, reference CUDA build on ONE B200 "
                                    "(it is single-GPU)" % n, "inputs_larger_than_l2": n >= 512}}
     if not ref_runner.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"})
         return
     import cuda_flow3d_b200 as pkg
     pkg.require_device()
@@ -183,7 +202,7 @@ def run_reference(args, rank, world):
                                         "the reference has no CPU implementation" % (len(t), n)},
                 e2e={"value": val, "unit": "Mvoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 gpu_launches=0, per_step_seconds=t)
-    print(json.dumps(base))
+    emit(base)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -320,7 +339,7 @@ def run_sharded(args, rank, world, local_rank):
         line["phase_ms_per_step_rank0"] = phases
         if e2e:
             line["e2e"] = e2e
-        print(json.dumps(line))
+        emit(line)
     dist.destroy_process_group()
 
 
@@ -509,7 +528,7 @@ def run_ours(args, rank, world, local_rank):
                 line["cpu_baseline"] = cpu_baseline_sample(n, solver_passes)
             except Exception as ex:  # the bench line must still print
                 line["cpu_baseline"] = {"error": repr(ex)}
-        print(json.dumps(line))
+        emit(line)
     L.flow3d_solver_destroy(solver)
     if dist is not None:
         dist.destroy_process_group()
@@ -520,6 +539,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    guard_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

@@ -33,7 +33,13 @@ class HostStreamedBackend:
     """CabiBackend stage calls on HOST tensors: upload operands, run, download results."""
     name = "cabi-streamed"
 
-    def __init__(self, device, gate, pinned=True):
+    def __init__(self, device, gate, pinned=True, cache_static=True):
+        # cache_static: keep a level's read-only solver inputs (fx,fy,fz,ft,u,v,w of this slab) on the
+        # device across its outer iterations instead of re-uploading them 40 times (7 of the 19 in-core
+        # volumes stay resident; switch off when even that does not fit)
+        self.cache_static = cache_static
+        self._static_key = None
+        self._static_dev = None
         self.inner = CabiBackend(device)
         self.dev = torch.device("cpu")
         self.cuda = self.inner.dev
@@ -135,8 +141,15 @@ class HostStreamedBackend:
         # every outer iteration and the alternate buffer is pure scratch (each sweep reads only planes
         # the previous sweep wrote), so those five fields exist on the device only.  Down: the iterate.
         with self._call():
-            dt = [self._up(t) for t in terms]
-            du, dv, dw = self._up_slab(u), self._up_slab(v), self._up_slab(w)
+            key = tuple(t.data_ptr() for t in terms) + (u.t.data_ptr(), v.t.data_ptr(), w.t.data_ptr())
+            if self.cache_static and self._static_key == key:
+                dt, du, dv, dw = self._static_dev
+            else:
+                self._static_key = self._static_dev = None  # frees the previous level's copies
+                dt = [self._up(t) for t in terms]
+                du, dv, dw = self._up_slab(u), self._up_slab(v), self._up_slab(w)
+                if self.cache_static:
+                    self._static_key, self._static_dev = key, (dt, du, dv, dw)
             dc = [self._up(t) for t in d_cur]
             da = [torch.empty_like(t) for t in dc]
             dphi, dksi = torch.empty_like(dc[0]), torch.empty_like(dc[0])
@@ -147,6 +160,7 @@ class HostStreamedBackend:
         return d_cur, d_alt
 
     def add3(self, flow, d):
+        self._static_key = self._static_dev = None  # the level's solver loop is over
         with self._call():
             df = [self._up_slab(f) for f in flow]
             self.inner.add3(df, [self._up(t) for t in d])
@@ -179,7 +193,8 @@ class OutOfCoreFlowSolver:
     does not fit the device: `slabs` virtual ranks streamed through one GPU."""
 
     def __init__(self, device=0, slabs=4, concurrency=2, pinned=True, backend_factory=None, frame_ghost=32,
-                 min_planes_per_slab=12, min_voxels_per_slab=1 << 18):
+                 min_planes_per_slab=12, min_voxels_per_slab=1 << 18, cache_static=True):
+        self.cache_static = cache_static
         self.device, self.slabs, self.concurrency, self.pinned = int(device), int(slabs), int(concurrency), pinned
         self.backend_factory = backend_factory  # tests: an OracleBackend per virtual rank (CPU)
         self.frame_ghost = frame_ghost
@@ -198,7 +213,7 @@ class OutOfCoreFlowSolver:
 
         def work(k):
             try:
-                be = self.backend_factory(k) if self.backend_factory else HostStreamedBackend(self.device, gate, self.pinned)
+                be = self.backend_factory(k) if self.backend_factory else HostStreamedBackend(self.device, gate, self.pinned, self.cache_static)
                 backends[k] = be
                 solver = ShardedFlowSolver(be, comm=LocalComm(shared, k), min_planes_per_rank=self.min_planes,
                                            min_voxels_per_rank=self.min_voxels)
