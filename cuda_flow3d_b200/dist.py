@@ -320,6 +320,16 @@ class TorchComm:
         for r in dist.batch_isend_irecv(p2p):
             r.wait()
 
+    def start_sendrecv(self, ops):
+        """post the operations and return at once (NCCL: they run on the communicator's stream after
+        the work already queued on the current stream); finish_sendrecv() orders later work after them"""
+        p2p = [dist.P2POp(dist.isend if kind == "send" else dist.irecv, t, peer) for kind, t, peer in ops]
+        return dist.batch_isend_irecv(p2p) if p2p else []
+
+    def finish_sendrecv(self, handle):
+        for r in handle:
+            r.wait()
+
     def allreduce_max(self, value, device):
         t = torch.tensor([value], dtype=torch.float32, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -362,6 +372,15 @@ class LocalComm:
                     except queue.Empty:
                         if self.sh.failed.is_set():
                             raise RuntimeError("a peer slab failed") from None
+
+    def start_sendrecv(self, ops):
+        for kind, t, peer in ops:
+            if kind == "send":
+                self.sh.box[(self.rank, peer)].put(t.clone())
+        return [op for op in ops if op[0] == "recv"]
+
+    def finish_sendrecv(self, handle):
+        self.sendrecv(handle)
 
     def _exchange_slot(self, value):
         self.sh.slots[self.rank] = value
@@ -494,7 +513,14 @@ class ShardedFlowSolver:
         self.world = self.comm.world
         self.min_planes = min_planes_per_rank
         self.min_voxels = min_voxels_per_rank
-        self.stats = {"sharded_levels": 0, "replicated_levels": 0, "exchanges": 0, "exchange_bytes": 0}
+        self.stats = {"sharded_levels": 0, "replicated_levels": 0, "exchanges": 0, "exchange_bytes": 0,
+                      "overlapped_levels": 0}
+        # Overlap of the per-outer-iteration halo exchange with compute (see _outer_loop_overlapped): pays
+        # when a rank talks to two neighbours and its slab is thin, i.e. from 4 ranks up; FLOW3D_OVERLAP=1/0
+        # forces it on/off
+        import os
+        env = os.environ.get("FLOW3D_OVERLAP", "")
+        self.overlap_min_world = 2 if env == "1" else (1 << 30) if env == "0" else 4
         self.profile = False      # record CUDA events around every batch of sweeps (CabiBackend only)
         self.sweep_events = []    # (start, end, voxel_sweeps, phi_ksi_voxels) per outer iteration
         self.phase_marks = []     # (phase name, CUDA event): time until the next mark belongs to the phase
@@ -642,24 +668,28 @@ class ShardedFlowSolver:
             d_cur = [be.zeros(w, hh, dl) for _ in range(3)]
             d_alt = [be.zeros(w, hh, dl) for _ in range(3)]
             phi, ksi = be.zeros(w, hh, dl), be.zeros(w, hh, dl)
-            for _ in range(outer):
-                self._mark("solver")
-                if prof:
-                    e0 = torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                d_cur, d_alt = be.outer_iteration(terms, flow[0], flow[1], flow[2], d_cur, d_alt, phi, ksi, h, inner,
-                                                  P["equation_alpha"], P["equation_smoothness"], P["equation_data"],
-                                                  lo1, hi1)
-                if prof:
-                    e1 = torch.cuda.Event(enable_timing=True)
-                    e1.record()
-                    units = 0
-                    for j in range(1, inner + 1):
-                        units += w * hh * ((hi1 if hi1 == d else hi1 - j) - (lo1 if lo1 == 0 else lo1 + j))
-                    self.sweep_events.append((e0, e1, units, w * hh * (hi1 - lo1)))
-                if sharded:
-                    self._mark("halo_exchange")
-                    self._exchange(d_cur, A, B, a, b, H, d)
+            use_overlap = (sharded and self.world >= self.overlap_min_world and d // self.world >= 4 * H
+                           and be.name != "cabi-streamed")
+            if use_overlap:
+                self.stats["overlapped_levels"] += 1
+                d_cur, d_alt = self._outer_loop_overlapped(terms, flow, d_cur, d_alt, phi, ksi, h, P, (A, B, a, b), d)
+            else:
+                for _ in range(outer):
+                    self._mark("solver")
+                    if prof:
+                        e0 = torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                    d_cur, d_alt = be.outer_iteration(terms, flow[0], flow[1], flow[2], d_cur, d_alt, phi, ksi, h,
+                                                      inner, P["equation_alpha"], P["equation_smoothness"],
+                                                      P["equation_data"], lo1, hi1)
+                    if prof:
+                        e1 = torch.cuda.Event(enable_timing=True)
+                        e1.record()
+                        self.sweep_events.append((e0, e1, self._sweep_units(w, hh, d, lo1, hi1, inner),
+                                                  w * hh * (hi1 - lo1)))
+                    if sharded:
+                        self._mark("halo_exchange")
+                        self._exchange(d_cur, A, B, a, b, H, d)
             self._mark("update")
             # ---- u += du (:420-438), valid on the whole buffer because the last exchange refreshed du ----
             be.add3(flow, d_cur)
@@ -682,6 +712,110 @@ class ShardedFlowSolver:
         if return_device:
             return a, b, [f.planes(a, b) for f in flow]
         return a, b, [be.to_numpy(f.planes(a, b), dims[0]) for f in flow]
+
+    @staticmethod
+    def _sweep_units(w, hh, d, lo1, hi1, inner):
+        units = 0
+        for j in range(1, inner + 1):
+            units += w * hh * ((hi1 if hi1 == d else hi1 - j) - (lo1 if lo1 == 0 else lo1 + j))
+        return units
+
+    def _outer_loop_overlapped(self, terms, flow, d_cur, d_alt, phi, ksi, h, P, ranges, d):
+        """The outer iterations of one sharded level with the halo exchange hidden behind compute.
+
+        The values an outer iteration produces at plane p depend on the iterate it starts from on
+        [p-H, p+H] only (phi: +-1, each of the `inner` sweeps: +-1; H = inner+1).  So the iteration splits
+        into an INTERIOR task, run on the owned planes [a,b) alone (final values valid on [a+H, b-H), no
+        ghost needed), and one BOUNDARY task per neighbour, run in a private 3H-plane buffer holding the
+        neighbour's H ghost planes and the adjacent 2H owned planes (final values valid on the H owned
+        planes next to the neighbour).  Per iteration: stage the 2H owned planes into the boundary
+        buffers, post the neighbour exchange (sends/receives use the boundary buffers only), run the
+        interior task while the planes travel, wait, run the boundary tasks, copy their H final planes
+        into the iterate.  Same kernels, same per-voxel arithmetic, same result as the serial scheme;
+        ~7 % more voxel-sweeps at 128 planes per rank."""
+        be = self.be
+        A, B, a, b = ranges
+        inner, outer = int(P["inner_iterations_count"]), int(P["outer_iterations_count"])
+        H = inner + 1
+        w, hh = flow[0].w, flow[0].t.shape[1]
+        alpha, eps_s, eps_d = P["equation_alpha"], P["equation_smoothness"], P["equation_data"]
+        prof = self.profile
+        sides = []  # (neighbour rank, region [rA, rB), ghost planes, owned planes to send, planes to copy back)
+        if a > A:
+            sides.append({"peer": self.rank - 1, "rA": A, "rB": a + 2 * H, "ghost": (A, a), "send": (a, a + H),
+                          "own": (a, a + 2 * H), "final": (a, a + H)})
+        if B > b:
+            sides.append({"peer": self.rank + 1, "rA": b - 2 * H, "rB": B, "ghost": (b, B), "send": (b - H, b),
+                          "own": (b - 2 * H, b), "final": (b - H, b)})
+        for sd in sides:
+            n = sd["rB"] - sd["rA"]
+            sd["cur"] = [be.zeros(w, hh, n) for _ in range(3)]
+            sd["alt"] = [be.zeros(w, hh, n) for _ in range(3)]
+            sd["phi"], sd["ksi"] = be.zeros(w, hh, n), be.zeros(w, hh, n)
+            o = sd["rA"] - A
+            sd["terms"] = [t[o:o + n] for t in terms]
+            sd["flow"] = [Slab(f.t[o:o + n], sd["rA"], d, w) for f in flow]
+            sd["lo1"] = sd["rA"] if sd["rA"] == 0 else sd["rA"] + 1
+            sd["hi1"] = sd["rB"] if sd["rB"] == d else sd["rB"] - 1
+        lo_int = 0 if a == 0 else a + 1   # interior task: the owned planes are its whole world
+        hi_int = d if b == d else b - 1
+        for it in range(outer):
+            handle = None
+            if it > 0:  # the first iteration starts from du = 0 everywhere: ghosts are zeros already
+                self._mark("halo_stage")
+                ops = []
+                for sd in sides:
+                    rA = sd["rA"]
+                    for c in range(3):
+                        sd["cur"][c][sd["own"][0] - rA:sd["own"][1] - rA].copy_(d_cur[c][sd["own"][0] - A:sd["own"][1] - A])
+                for c in range(3):  # field-major order on both sides of a link, as in _exchange
+                    for sd in sides:
+                        rA = sd["rA"]
+                        g0, g1 = sd["ghost"]
+                        s0, s1 = sd["send"]
+                        if sd["peer"] < self.rank:
+                            ops.append(("recv", sd["cur"][c][g0 - rA:g1 - rA], sd["peer"]))
+                            ops.append(("send", sd["cur"][c][s0 - rA:s1 - rA], sd["peer"]))
+                        else:
+                            ops.append(("send", sd["cur"][c][s0 - rA:s1 - rA], sd["peer"]))
+                            ops.append(("recv", sd["cur"][c][g0 - rA:g1 - rA], sd["peer"]))
+                handle = self.comm.start_sendrecv(ops)
+                self.stats["exchanges"] += 1
+                self.stats["exchange_bytes"] += sum(t.numel() * 4 for kind, t, _ in ops if kind == "send")
+            self._mark("solver")
+            if prof:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+            d_cur, d_alt = be.outer_iteration(terms, flow[0], flow[1], flow[2], d_cur, d_alt, phi, ksi, h, inner, alpha,
+                                              eps_s, eps_d, lo_int, hi_int)
+            if prof:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                self.sweep_events.append((e0, e1, self._sweep_units(w, hh, d, lo_int, hi_int, inner),
+                                          w * hh * (hi_int - lo_int)))
+            if handle is not None:
+                self._mark("halo_wait")
+                self.comm.finish_sendrecv(handle)
+            self._mark("solver_boundary")
+            for sd in sides:
+                if prof:
+                    e0 = torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                sd["cur"], sd["alt"] = be.outer_iteration(sd["terms"], sd["flow"][0], sd["flow"][1], sd["flow"][2],
+                                                          sd["cur"], sd["alt"], sd["phi"], sd["ksi"], h, inner, alpha,
+                                                          eps_s, eps_d, sd["lo1"], sd["hi1"])
+                f0, f1 = sd["final"]
+                for c in range(3):
+                    d_cur[c][f0 - A:f1 - A].copy_(sd["cur"][c][f0 - sd["rA"]:f1 - sd["rA"]])
+                if prof:
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    e1.record()
+                    self.sweep_events.append((e0, e1, self._sweep_units(w, hh, d, sd["lo1"], sd["hi1"], inner),
+                                              w * hh * (sd["hi1"] - sd["lo1"])))
+        # the update, the median and the next prolongation read the iterate's ghost planes
+        self._mark("halo_exchange")
+        self._exchange(d_cur, A, B, a, b, H, d)
+        return d_cur, d_alt
 
     def sweep_profile(self):
         """(milliseconds, voxel-sweeps, phi/ksi voxel-updates) of the recorded outer iterations (each

@@ -21,8 +21,10 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, shape, params, out_dir, slabs=False):
+def _worker(rank, world, port, shape, params, out_dir, slabs=False, overlap=None):
     import sys
+    if overlap is not None:
+        os.environ["FLOW3D_OVERLAP"] = "1" if overlap else "0"
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -46,7 +48,7 @@ def _worker(rank, world, port, shape, params, out_dir, slabs=False):
         a, b, flow = solver.compute(f0, f1, params)
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), a=a, b=b, u=flow[0], v=flow[1], w=flow[2],
              sharded=solver.stats["sharded_levels"], exchanges=solver.stats["exchanges"],
-             gathers=solver.stats.get("frame_gathers", 0))
+             gathers=solver.stats.get("frame_gathers", 0), overlapped=solver.stats["overlapped_levels"])
     dist.destroy_process_group()
 
 
@@ -71,6 +73,32 @@ def test_two_rank_sharded_solve_equals_single_process(oracle, tmp_path, shape, p
         assert int(z["exchanges"]) > 0
         if slabs and params["warp_levels_count"] >= 12:
             assert int(z["gathers"]) > 0, "coarse levels must have used the all-gather path"
+        for c, name in enumerate("uvw"):
+            assert np.array_equal(z[name], ref[c][a:b]), "rank %d flow_%s planes [%d,%d) differ" % (r, name, a, b)
+        covered += b - a
+    assert covered == shape[0]
+
+
+@pytest.mark.parametrize("world,shape,params,slabs", [
+    (3, (54, 14, 16), dict(outer_iterations_count=3, inner_iterations_count=2, warp_levels_count=5, median_radius=3,
+                           warp_scale_factor=0.9), False),
+    (4, (64, 12, 14), dict(outer_iterations_count=2, inner_iterations_count=2, warp_levels_count=4, median_radius=5,
+                           warp_scale_factor=0.9, gaussian_sigma=1.0), True),
+])
+def test_overlapped_halo_exchange_equals_single_process(oracle, tmp_path, world, shape, params, slabs):
+    """boundary-first / interior split of the outer iteration (ShardedFlowSolver._outer_loop_overlapped):
+    interior ranks with two neighbours, edge ranks with one; forced on for world 3, default policy for 4"""
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, shape, params, str(tmp_path), slabs, True if world < 4 else None),
+             nprocs=world, join=True)
+    f0 = smooth_volume(shape, 21)
+    f1 = np.ascontiguousarray(np.roll(f0, (1, -1, 2), axis=(0, 1, 2)))
+    ref = oracle.compute_flow(f0, f1, params)
+    covered = 0
+    for r in range(world):
+        z = np.load(os.path.join(str(tmp_path), "rank%d.npz" % r))
+        a, b = int(z["a"]), int(z["b"])
+        assert int(z["overlapped"]) >= 1, "the test must exercise the overlapped outer loop"
         for c, name in enumerate("uvw"):
             assert np.array_equal(z[name], ref[c][a:b]), "rank %d flow_%s planes [%d,%d) differ" % (r, name, a, b)
         covered += b - a
