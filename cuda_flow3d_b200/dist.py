@@ -515,12 +515,13 @@ class ShardedFlowSolver:
         self.min_voxels = min_voxels_per_rank
         self.stats = {"sharded_levels": 0, "replicated_levels": 0, "exchanges": 0, "exchange_bytes": 0,
                       "overlapped_levels": 0}
-        # Overlap of the per-outer-iteration halo exchange with compute (see _outer_loop_overlapped): pays
-        # when a rank talks to two neighbours and its slab is thin, i.e. from 4 ranks up; FLOW3D_OVERLAP=1/0
-        # forces it on/off
+        # Overlap of the per-outer-iteration halo exchange with compute (see _outer_loop_overlapped).
+        # Opt-in (FLOW3D_OVERLAP=1): measured on 2 B200s at 512^3 it hides the exchange (118-190 ms -> 36 ms
+        # of waits) but the short boundary launches (6..16 planes) run ~3x less efficiently than the
+        # interior ones and cost 200 ms + 70 ms of staging copies, a net loss there (2.13 s vs 1.97-2.12 s).
         import os
         env = os.environ.get("FLOW3D_OVERLAP", "")
-        self.overlap_min_world = 2 if env == "1" else (1 << 30) if env == "0" else 4
+        self.overlap_min_world = 2 if env == "1" else (1 << 30)
         self.profile = False      # record CUDA events around every batch of sweeps (CabiBackend only)
         self.sweep_events = []    # (start, end, voxel_sweeps, phi_ksi_voxels) per outer iteration
         self.phase_marks = []     # (phase name, CUDA event): time until the next mark belongs to the phase

@@ -87,9 +87,9 @@ def test_two_rank_sharded_solve_equals_single_process(oracle, tmp_path, shape, p
 ])
 def test_overlapped_halo_exchange_equals_single_process(oracle, tmp_path, world, shape, params, slabs):
     """boundary-first / interior split of the outer iteration (ShardedFlowSolver._outer_loop_overlapped):
-    interior ranks with two neighbours, edge ranks with one; forced on for world 3, default policy for 4"""
+    interior ranks with two neighbours, edge ranks with one; opt-in path (FLOW3D_OVERLAP=1)"""
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, shape, params, str(tmp_path), slabs, True if world < 4 else None),
+    mp.spawn(_worker, args=(world, port, shape, params, str(tmp_path), slabs, True),
              nprocs=world, join=True)
     f0 = smooth_volume(shape, 21)
     f1 = np.ascontiguousarray(np.roll(f0, (1, -1, 2), axis=(0, 1, 2)))
