@@ -9,6 +9,7 @@ tail -3 $O/${TAG}_pytest.log
 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err
 cat $O/${TAG}_bench.json | cut -c1-600
 if [ "$2" = "full" ]; then
+  # NOTE: the full 40-level launch list takes >25 min under ncu; scripts/gpu_profiles.sh profiles the two finest levels instead
   python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > $O/${TAG}_plain_launch.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum --clock-control none -s 10400 -c 10500 --csv --log-file $O/${TAG}_launches.csv \
     python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > $O/${TAG}_ncu_launch.log 2>&1
