@@ -79,18 +79,19 @@ def test_two_rank_sharded_solve_equals_single_process(oracle, tmp_path, shape, p
     assert covered == shape[0]
 
 
+@pytest.mark.parametrize("overlap", [True, False])
 @pytest.mark.parametrize("world,shape,params,slabs", [
     (3, (54, 14, 16), dict(outer_iterations_count=3, inner_iterations_count=2, warp_levels_count=5, median_radius=3,
                            warp_scale_factor=0.9), False),
     (4, (64, 12, 14), dict(outer_iterations_count=2, inner_iterations_count=2, warp_levels_count=4, median_radius=5,
                            warp_scale_factor=0.9, gaussian_sigma=1.0), True),
 ])
-def test_overlapped_halo_exchange_equals_single_process(oracle, tmp_path, world, shape, params, slabs):
-    """boundary-first / interior split of the outer iteration (ShardedFlowSolver._outer_loop_overlapped):
-    interior ranks with two neighbours, edge ranks with one; opt-in path (FLOW3D_OVERLAP=1)"""
+def test_more_ranks_with_and_without_overlapped_exchange(oracle, tmp_path, world, shape, params, slabs, overlap):
+    """world 3 and 4 (interior ranks with two neighbours, edge ranks with one): the default serial exchange
+    and the opt-in boundary-first / interior split of the outer iteration
+    (ShardedFlowSolver._outer_loop_overlapped, FLOW3D_OVERLAP=1) both reproduce the single-process solve"""
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, shape, params, str(tmp_path), slabs, True),
-             nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, shape, params, str(tmp_path), slabs, overlap), nprocs=world, join=True)
     f0 = smooth_volume(shape, 21)
     f1 = np.ascontiguousarray(np.roll(f0, (1, -1, 2), axis=(0, 1, 2)))
     ref = oracle.compute_flow(f0, f1, params)
@@ -98,7 +99,8 @@ def test_overlapped_halo_exchange_equals_single_process(oracle, tmp_path, world,
     for r in range(world):
         z = np.load(os.path.join(str(tmp_path), "rank%d.npz" % r))
         a, b = int(z["a"]), int(z["b"])
-        assert int(z["overlapped"]) >= 1, "the test must exercise the overlapped outer loop"
+        assert int(z["sharded"]) >= 1
+        assert (int(z["overlapped"]) >= 1) == overlap, "overlap flag not honoured"
         for c, name in enumerate("uvw"):
             assert np.array_equal(z[name], ref[c][a:b]), "rank %d flow_%s planes [%d,%d) differ" % (r, name, a, b)
         covered += b - a
