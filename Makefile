@@ -9,7 +9,7 @@ NVFLAGS   := $(ARCH) -ccbin $(HOSTCXX) -std=c++17 -O3 -lineinfo -fmad=false -Xco
 PKG       := cuda_flow3d_b200
 CSRC      := $(PKG)/csrc
 LIB       := $(PKG)/libflow3d_b200.so
-CU_SRCS   := $(CSRC)/flow3d_cabi.cu $(CSRC)/kernels_solve.cu $(CSRC)/kernels_pyramid.cu \
+CU_SRCS   := $(CSRC)/flow3d_cabi.cu $(CSRC)/kernels_solve.cu $(CSRC)/kernels_sweep_tma.cu $(CSRC)/kernels_pyramid.cu \
              $(CSRC)/kernels_warp.cu $(CSRC)/kernels_median.cu $(CSRC)/kernels_synth.cu \
              $(CSRC)/kernels_diag.cu
 CU_OBJS   := $(CU_SRCS:.cu=.o)
@@ -26,7 +26,7 @@ $(CSRC)/median5_sort25.inc: scripts/gen_median5_pair.py
 $(CSRC)/median_net_%.inc: scripts/gen_median_network.py
 	python3 scripts/gen_median_network.py $* $@
 
-%.o: %.cu $(CSRC)/common.cuh include/flow3d_c.h
+%.o: %.cu $(CSRC)/common.cuh $(CSRC)/solve_args.cuh include/flow3d_c.h
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; exit 1)
 
 $(PKG)/host/%.o: $(PKG)/host/%.cpp
@@ -39,8 +39,12 @@ oracle:
 	$(MAKE) -C oracle liboracle.so
 
 # example programs against the reference-shaped C++ host API
-APPS := build/flow3d_cli build/example_main
+APPS := build/flow3d_cli build/example_main build/flow3d_synth
 apps: $(APPS)
+# standalone input generator for bench.py's reference arm: the synth kernel compiled in, NOT linked to $(LIB)
+build/flow3d_synth: apps/flow3d_synth.cu $(CSRC)/kernels_synth.cu $(CSRC)/common.cuh
+	@mkdir -p build
+	$(NVCC) $(ARCH) -ccbin $(HOSTCXX) -std=c++17 -O3 -fmad=false -Iinclude -I$(CSRC) $< -o $@
 build/%: apps/%.cpp $(LIB)
 	@mkdir -p build
 	$(HOSTCXX) -std=c++17 -O2 -Iinclude $< -o $@ -L$(PKG) -lflow3d_b200 -Wl,-rpath,'$$ORIGIN/../$(PKG)'

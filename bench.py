@@ -34,6 +34,66 @@ SEED = 20240521
 _REAL_STDOUT = None
 
 
+def workload_name(n):
+    """ONE string for both arms (the driver compares config.workload of the two lines)"""
+    return ("synthetic %d^3 pair with known rigid motion (BASELINE configs[2]), default parameters: "
+            "warp_levels_count 40, scale 0.95, 40 outer x 5 inner sweeps, median 5, sigma 2" % n)
+
+
+def sha256_file(path, chunk=1 << 24):
+    import hashlib
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        while True:
+            b = f.read(chunk)
+            if not b:
+                break
+            h.update(b)
+    return h.hexdigest()
+
+
+def sha256_array(a):
+    import hashlib
+    return hashlib.sha256(memoryview(np.ascontiguousarray(a)).cast("B")).hexdigest()
+
+
+def shipped_pairs():
+    """The reference's two shipped pairs (BASELINE configs[0], configs[1]) from tests/golden/data (xz),
+    as uint8 volumes (D,H,W) -- what ReadRAWFromFileU8 reads -- plus the sha256 of the flows the
+    reference's own CUDA build produced for them on a B200 (tests/golden/reference_flows.json) and the
+    algorithmic bytes of a default solve."""
+    import lzma
+    g = os.path.join(ROOT, "tests", "golden")
+    meta = json.load(open(os.path.join(g, "reference_flows.json")))
+
+    def xz(name):
+        with lzma.open(os.path.join(g, "data", name), "rb") as f:
+            return f.read()
+    out = []
+    a = [np.frombuffer(xz("frame_%d_128-128-128.raw.xz" % i), np.uint8).reshape(128, 128, 128) for i in (0, 1)]
+    out.append({"name": "shipped 128^3 pair (BASELINE configs[0])", "key": "pair128", "frames": a, "guarded": False,
+                "algorithmic_bytes": 1.828e11, "sha": meta["pair128"]["full_sha256"]})
+    b = [np.ascontiguousarray(np.broadcast_to(np.frombuffer(xz("%s-584-388-slice.raw.xz" % n), np.uint8)
+                                              .reshape(388, 584), (5, 388, 584))) for n in ("rub1", "rub2")]
+    out.append({"name": "shipped 584x388x5 slab pair (BASELINE configs[1])", "key": "slab", "frames": b,
+                "guarded": True, "algorithmic_bytes": 8.436e10, "sha": meta["slab"]["full_sha256"]})
+    return out
+
+
+def scratch_dir(need_bytes):
+    """a tmp dir with room for need_bytes: /dev/shm when it is large enough, else the default tmp"""
+    import shutil
+    for base in ("/dev/shm", None):
+        try:
+            d = tempfile.mkdtemp(prefix="f3dbench_", dir=base)
+            if shutil.disk_usage(d).free > need_bytes * 1.1:
+                return d
+            shutil.rmtree(d, ignore_errors=True)
+        except Exception:
+            continue
+    return tempfile.mkdtemp(prefix="f3dbench_")
+
+
 def guard_stdout():
     """Everything libraries print to fd 1 (NCCL's version banner, torchrun notes) goes to stderr; the one
     JSON line is written to the real stdout by emit()."""
@@ -59,6 +119,7 @@ def parse():
     ap.add_argument("--size", type=int, default=0, help="cube edge (default 512)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the shipped-pair extra_configs")
     ap.add_argument("--levels", type=int, default=0,
                     help="profiling aid: run only the finest LEVELS pyramid levels (NOT the benchmark workload; the "
                          "JSON line says so)")
@@ -171,37 +232,80 @@ def level_voxel_sum(pkg, W, H, D, P):
 
 # ---------------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
-    """The reference's own CUDA build (the reference has no CPU path), one process on rank 0."""
+    """The reference's own CUDA build (the reference has no CPU path), one process on rank 0.
+
+    This arm never imports cuda_flow3d_b200 and never maps libflow3d_b200.so: the synthetic pair is
+    written by the standalone generator build/flow3d_synth (separate process, synth kernel compiled in)
+    and solved by oracle/_ref/flow3d_ref (separate process, unmodified reference sources)."""
     if rank != 0:
         return
+    import shutil
     from oracle import ref_runner
     n = args.size or 512
     base = {"impl": "reference", "metric": "Mvoxel/s per full pyramid flow solve", "unit": "Mvoxel/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
             "dtype": "f32", "data": "synthetic", "scaling": "weak", "vs_baseline": None,
-            "config": {"workload": "synthetic %d^3 pair, default parameters, reference CUDA build on ONE B200 "
-                                   "(it is single-GPU)" % n, "inputs_larger_than_l2": n >= 512}}
+            "config": {"workload": workload_name(n), "parallelism": "1 GPU",
+                       "inputs_larger_than_l2": bool(n ** 3 * 4 > 126e6)}}
+    gen = os.path.join(ROOT, "build", "flow3d_synth")
     if not ref_runner.available():
         emit({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"})
         return
-    import cuda_flow3d_b200 as pkg
-    pkg.require_device()
-    f0, f1, _ = pkg.ops.synth_pair(n, n, n, SEED, truth=False)
-    warm = min(args.warmup, 1)  # module load/JIT is outside ComputeFlow; one warm solve is enough
-    sampler = ClockSampler(0)
-    sampler.start()
-    _, _, _, times, _ = ref_runner.run_reference(f0, f1, reps=warm + args.steps, want_output=False, timeout=6000)
-    clocks = sampler.stop()
+    if not os.path.exists(gen):
+        emit({"impl": "reference", "unavailable": "build/flow3d_synth missing (make apps)"})
+        return
+    tmp = scratch_dir(5 * 4 * n ** 3)
+    try:
+        p0, p1 = os.path.join(tmp, "f0.raw"), os.path.join(tmp, "f1.raw")
+        subprocess.run([gen, str(n), str(n), str(n), str(SEED), p0, p1], check=True, timeout=1200)
+        # one solve alone first: its time bounds how many warm-up solves fit the budget
+        t_first, _ = ref_runner.run_reference_files(p0, p1, (n, n, n), reps=1, timeout=6000)
+        budget_s = float(os.environ.get("FLOW3D_REF_BUDGET_S", "780"))
+        warm = max(0, min(args.warmup - 1, int(budget_s / max(t_first[0], 1e-3)) - args.steps - 1))
+        prefix = os.path.join(tmp, "flow")
+        sampler = ClockSampler(0)
+        sampler.start()
+        times, _ = ref_runner.run_reference_files(p0, p1, (n, n, n), reps=warm + args.steps, out_prefix=prefix,
+                                                  timeout=6000)
+        clocks = sampler.stop()
+        sha = {c: sha256_file(prefix + "_%s.raw" % c) for c in "uvw"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
     t = times[warm:]
     ms = 1000.0 * float(np.mean(t))
     val = n ** 3 / (ms / 1000.0) / 1e6
-    base.update(value=val, ms_per_step=ms, clocks=clocks,
+    base.update(value=val, ms_per_step=ms, clocks=clocks, warmup=warm + 1, warmup_requested=args.warmup,
+                flow_sha256=sha,
                 cpu_baseline={"value": val, "unit": "Mvoxel/s", "cores": 1, "kind": "reference",
                               "sample": "unmodified reference sources (oracle/build_ref.sh), %d full solves of the "
-                                        "%d^3 pair on the B200, host-timed around ComputeFlow (H2D+levels+D2H); "
-                                        "the reference has no CPU implementation" % (len(t), n)},
+                                        "%d^3 pair on the B200 after %d warm-up solves (one in its own process), "
+                                        "host-timed around ComputeFlow (H2D+levels+D2H); the reference has no CPU "
+                                        "implementation" % (len(t), n, warm + 1)},
                 e2e={"value": val, "unit": "Mvoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 gpu_launches=0, per_step_seconds=t)
+    if not args.no_extra:
+        extra = []
+        for pr in shipped_pairs():
+            tmp = scratch_dir(64 << 20)
+            try:
+                d, h, w = pr["frames"][0].shape
+                q0, q1 = os.path.join(tmp, "a.raw"), os.path.join(tmp, "b.raw")
+                pr["frames"][0].tofile(q0)
+                pr["frames"][1].tofile(q1)
+                pre = os.path.join(tmp, "flow")
+                ts, _ = ref_runner.run_reference_files(q0, q1, (w, h, d), reps=4, out_prefix=pre, u8=True,
+                                                       guarded=pr["guarded"], timeout=1200)
+                sh = {c: sha256_file(pre + "_%s.raw" % c) for c in "uvw"}
+                extra.append({"workload": pr["name"], "ms_per_solve": 1000.0 * float(np.mean(ts[1:])),
+                              "solves_timed": len(ts) - 1, "flow_sha256": sh,
+                              "matches_golden_sha256": sh == pr["sha"],
+                              "kernels": "guarded PTX (the as-shipped kernels fault on this pair, DESIGN.md 2)"
+                              if pr["guarded"] else "as shipped"})
+            except Exception as ex:
+                extra.append({"workload": pr["name"], "error": repr(ex)[:300]})
+            finally:
+                shutil.rmtree(tmp, ignore_errors=True)
+        base["extra_configs"] = extra
     emit(base)
 
 
@@ -343,6 +447,46 @@ def run_sharded(args, rank, world, local_rank):
     dist.destroy_process_group()
 
 
+def extra_shipped_pairs(pkg, L, device, peak):
+    """BASELINE configs[0] and configs[1] through the host call (H2D + solve + D2H, CUDA events inside the
+    library = the reference's own bracket): ms per solve, sha256 against the flows of the reference's own
+    CUDA build (tests/golden/reference_flows.json), and the whole-solve algorithmic bytes / time."""
+    out = []
+    for pr in shipped_pairs():
+        try:
+            f0, f1 = [np.ascontiguousarray(a.astype(np.float32)) for a in pr["frames"]]
+            d, h, w = f0.shape
+            solver = C.c_void_p()
+            pkg._lib.check(L.flow3d_solver_create(w, h, d, device, C.byref(solver)), "solver_create")
+            params = pkg.api.make_params(None)
+            outs = [np.zeros_like(f0) for _ in range(3)]
+            ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+            times = []
+            if hasattr(L, "flow3d_solver_tune"):
+                pkg._lib.check(L.flow3d_solver_tune(solver, C.byref(params)), "tune")
+            for i in range(5):
+                pkg._lib.check(L.flow3d_solver_compute_host(solver, ptr(f0), ptr(f1), C.byref(params), ptr(outs[0]),
+                                                            ptr(outs[1]), ptr(outs[2])), "compute_host")
+                ms2 = (C.c_float * 2)()
+                L.flow3d_solver_last_timing(solver, ms2)
+                times.append(float(ms2[0]))
+            L.flow3d_solver_destroy(solver)
+            ms = float(np.mean(times[2:]))
+            sh = {c: sha256_array(o) for c, o in zip("uvw", outs)}
+            ach = pr["algorithmic_bytes"] / (ms / 1000.0) / 1e9
+            out.append({"workload": pr["name"], "ms_per_solve": ms, "solves_timed": len(times) - 2,
+                        "host_memory": "pageable numpy (as the reference's Data3D)",
+                        "Mvoxel_per_s": w * h * d / (ms / 1000.0) / 1e6, "flow_sha256": sh,
+                        "matches_reference_build_sha256": sh == pr["sha"],
+                        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                                     "frac": ach / peak if peak else None,
+                                     "note": "whole-solve algorithmic bytes (SURVEY.md 8d) / time; the levels of "
+                                             "these pairs fit L2, so this is a latency-bound workload"}})
+        except Exception as ex:
+            out.append({"workload": pr["name"], "error": repr(ex)[:300]})
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     if world > 1 and not args.replicas:
         return run_sharded(args, rank, world, local_rank)
@@ -378,6 +522,10 @@ def run_ours(args, rank, world, local_rank):
     solver = C.c_void_p()
     pkg._lib.check(L.flow3d_solver_create(W, H, D, local_rank, C.byref(solver)), "solver_create")
     pkg._lib.check(L.flow3d_solver_set_profiling(solver, 1), "profiling")
+    # launch shapes are tuned explicitly, before any timing (synchronous; the solves below never tune)
+    t_tune = time.perf_counter()
+    pkg._lib.check(L.flow3d_solver_tune(solver, C.byref(params)), "solver_tune")
+    t_tune = time.perf_counter() - t_tune
 
     def step_device():
         pkg._lib.check(L.flow3d_solver_compute_device(
@@ -425,6 +573,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- e2e: the reference-shaped host call with pinned HOST buffers (H2D + D2H inside) ------------
     e2e = None
+    flow_sha = None
     if not args.no_e2e:
         h0 = torch.empty((D, H, W), dtype=torch.float32, pin_memory=True)
         h1 = torch.empty((D, H, W), dtype=torch.float32, pin_memory=True)
@@ -462,6 +611,8 @@ def run_ours(args, rank, world, local_rank):
         pkg._lib.check(L.flow3d_download(C.c_void_p(outs[0].data_ptr()), C.c_void_p(chk.data_ptr()), dims, ld, sp), "dl")
         torch.cuda.synchronize()
         e2e["host_equals_device_result"] = bool(torch.equal(chk, ho[0]))
+        if rank == 0:
+            flow_sha = {c: sha256_array(ho[i].numpy()) for i, c in enumerate("uvw")}
 
     # ---- accuracy: endpoint error of the computed flow against the analytic ground truth ------------
     epe = None
@@ -501,14 +652,14 @@ def run_ours(args, rank, world, local_rank):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "synthetic %d^3 pair with known rigid motion (BASELINE configs[2]), default "
-                                   "parameters: %d levels x 40 outer x 5 inner sweeps, median 5, sigma 2" % (n, nlev),
-                       "reduced_levels_profiling_run": args.levels if args.levels > 0 else None,
+            "config": {"workload": workload_name(n),
                        "parallelism": "1 GPU" if world == 1 else "%d independent replicas (one volume pair per GPU)" % world,
-                       "inputs_larger_than_l2": bool(vol * 4 > 126e6), "level_voxels": nsum,
-                       "parity": "bit-identical to the reference CUDA build (tests/)"},
-            "clocks": clocks, "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "sweep_kernel (one Jacobi sweep)", "achieved": achieved,
+                       "inputs_larger_than_l2": bool(W * H * D * 4 > 126e6),
+                       "reduced_levels_profiling_run": args.levels if args.levels > 0 else None,
+                       "pyramid_levels": nlev, "level_voxels": nsum},
+            "clocks": clocks, "gpu_launches": launches, "tune_seconds_untimed": t_tune,
+            "roofline": {"bound": "hbm", "kernel": "Jacobi sweep launches (sweep_tma_kernel / sweep_kernel, per level "
+                                                    "as tuned)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_voxel_sweep": SWEEP_BYTES,
@@ -520,8 +671,14 @@ def run_ours(args, rank, world, local_rank):
         }
         if e2e:
             line["e2e"] = e2e
+        if flow_sha:
+            # sha256 of the tight float32 u/v/w volumes of the e2e solve; the reference arm prints the same
+            # for the same synthetic pair (bit parity at the headline size is a comparison of the two lines)
+            line["flow_sha256"] = flow_sha
         if epe:
             line["endpoint_error"] = epe
+        if world == 1 and not args.no_extra and args.levels == 0:
+            line["extra_configs"] = extra_shipped_pairs(pkg, L, local_rank, peak)
         if world == 1 and not args.no_cpu_baseline:
             solver_passes = nsum * (P["outer_iterations_count"] * (1 + P["inner_iterations_count"]))
             try:

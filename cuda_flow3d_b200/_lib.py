@@ -90,6 +90,8 @@ SIGNATURES = {
     "flow3d_median": (C.c_int, [_vp, _vp, _sz3, C.c_size_t, C.c_size_t, _vp]),
     "flow3d_gauss_blur_slab": (C.c_int, [_vp, _vp, _vp, _sz3, C.c_size_t, C.POINTER(ZSlab), C.c_float, _vp]),
     "flow3d_sweep_slab": (C.c_int, [_vp] * 12 + [_sz3, C.c_size_t, C.POINTER(ZSlab), _f3, C.c_float] + [_vp] * 4),
+    "flow3d_sweep_shape": (C.c_int, [_vp] * 12 + [_sz3, C.c_size_t, C.POINTER(ZSlab), _f3, C.c_float, C.c_float] +
+                           [_vp] * 4 + [C.c_int] * 3 + [_vp]),
     "flow3d_phi_ksi_slab": (C.c_int, [_vp] * 10 + [_sz3, C.c_size_t, C.POINTER(ZSlab), _f3, C.c_float, C.c_float] + [_vp] * 3),
     "flow3d_warp_derivatives_slab": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp, _vp, _vp, _sz3, C.c_size_t,
                                                C.POINTER(ZSlab), _f3] + [_vp] * 5),
@@ -105,6 +107,9 @@ SIGNATURES = {
     "flow3d_solver_compute_host": (C.c_int, [_vp, _vp, _vp, C.POINTER(Params), _vp, _vp, _vp]),
     "flow3d_solver_compute_device": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.POINTER(Params), _vp, _vp,
                                                _vp, _vp]),
+    "flow3d_solver_tune": (C.c_int, [_vp, C.POINTER(Params)]),
+    "flow3d_tune_kernels": (C.c_int, [_sz3, C.c_size_t, C.POINTER(ZSlab), _f3, _vp, C.c_size_t, _vp]),
+    "flow3d_tune_query": (C.c_int, [C.c_int, _sz3, C.c_size_t, C.POINTER(ZSlab), C.c_int * 3]),
     "flow3d_solver_last_timing": (C.c_int, [_vp, C.c_float * 2]),
     "flow3d_solver_set_profiling": (C.c_int, [_vp, C.c_int]),
     "flow3d_solver_stage_times": (C.c_int, [_vp, C.c_float * 8, C.c_double * 8, C.c_uint64 * 8]),
@@ -114,6 +119,7 @@ SIGNATURES = {
     "flow3d_solver_set_diagnostics": (C.c_int, [_vp, C.c_int, C.c_float]),
     "flow3d_solver_diagnostics": (C.c_int, [_vp, C.POINTER(C.c_size_t), _vp, _vp, _vp, C.c_size_t,
                                             C.POINTER(C.c_size_t)]),
+    "flow3d_selftest_fast_div": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int, C.c_uint64 * 3]),
     "flow3d_synth_pair": (C.c_int, [C.c_size_t] * 6 + [C.c_uint64] + [_vp] * 6),
 }
 

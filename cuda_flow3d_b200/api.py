@@ -247,6 +247,22 @@ class _Ops:
                              None), "flow3d_sweep")
         return [t.numpy() for t in o]
 
+    def sweep_shape(self, fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, h, alpha, eps_d, variant, vec, nchunks,
+                    fused_ksi=False, slab=None):
+        """one sweep with an explicit launch shape / kernel variant (flow3d_sweep_shape); returns
+        [du, dv, dw, ksi_out or None], or None when the variant cannot run this level"""
+        L = load()
+        d = self._dv(fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi)
+        o = [DeviceVolume.zeros(d[0].dims) for _ in range(3)]
+        ko = DeviceVolume.zeros(d[0].dims) if fused_ksi else None
+        rc = L.flow3d_sweep_shape(*[t.ptr for t in d], sz3(d[0].dims), d[0].ld, C.byref(slab) if slab else None,
+                                  f3(h), alpha, eps_d, *[t.ptr for t in o], ko.ptr if ko else None, variant, vec,
+                                  nchunks, None)
+        if rc == _lib.ERR_UNSUPPORTED:
+            return None
+        check(rc, "flow3d_sweep_shape")
+        return [t.numpy() for t in o] + [ko.numpy() if ko else None]
+
     def solve_level(self, fx, fy, fz, ft, u, v, w, h, outer, inner, alpha, eps_s, eps_d):
         L = load()
         d = self._dv(fx, fy, fz, ft, u, v, w)

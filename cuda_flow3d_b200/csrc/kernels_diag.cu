@@ -101,4 +101,68 @@ int launch_update_norm(const float* a0, const float* a1, const float* a2, const 
   return check_launch("update_norm_kernel");
 }
 
+// ------------------------------------------------------------------------------------------------
+// self-test of the branch-free division (common.cuh: div_fast) against __fdiv_rn, on the device (the
+// sequence starts from MUFU.RCP, which has no host equivalent).  mode 0: random sign / exponent in
+// [2^-60, 2^60) / mantissa for both operands; mode 1: EVERY divisor mantissa (2^23) against a handful
+// of dividends per launch slice.  out[0] = mismatching quotients among accepted pairs, out[1] = pairs
+// the range flag rejected, out[2] = pairs tested.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__device__ __forceinline__ float make_operand(unsigned long long r) {
+  const unsigned mant = (unsigned)(r & 0x7fffffu);
+  const unsigned ex = 67u + (unsigned)((r >> 23) % 120u);  // 2^-60 .. 2^59
+  const unsigned sign = (unsigned)((r >> 40) & 1u) << 31;
+  return __uint_as_float(sign | (ex << 23) | mant);
+}
+__global__ void __launch_bounds__(256) fast_div_selftest_kernel(unsigned long long n, unsigned long long seed, int mode,
+                                                                unsigned long long* out) {
+  unsigned long long bad = 0, rejected = 0, tested = 0;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    float a, b;
+    if (mode == 0) {
+      a = make_operand(mix64(seed + 2 * i));
+      b = make_operand(mix64(seed + 2 * i + 1));
+    } else {
+      a = make_operand(mix64(seed + (i >> 23)));
+      b = __uint_as_float((127u << 23) | (unsigned)(i & 0x7fffffu));
+      if ((i >> 23) & 1) b = -b;
+    }
+    bool ok = true;
+    const float q = div_fast(a, b, ok);
+    const float ref = __fdiv_rn(a, b);
+    ++tested;
+    if (!ok) ++rejected;
+    else if (__float_as_uint(q) != __float_as_uint(ref)) ++bad;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    rejected += __shfl_xor_sync(0xffffffffu, rejected, o);
+    tested += __shfl_xor_sync(0xffffffffu, tested, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out + 0, bad);
+    atomicAdd(out + 1, rejected);
+    atomicAdd(out + 2, tested);
+  }
+}
+
+int launch_fast_div_selftest(unsigned long long n, unsigned long long seed, int mode, unsigned long long out_host[3]) {
+  unsigned long long* dev = nullptr;
+  cudaError_t e = cudaMalloc(&dev, 3 * sizeof(unsigned long long));
+  if (e != cudaSuccess) { note_cuda_error(e, "cudaMalloc"); return FLOW3D_ERR_CUDA; }
+  cudaMemset(dev, 0, 3 * sizeof(unsigned long long));
+  fast_div_selftest_kernel<<<sm_count() * 8, 256>>>(n, seed, mode, dev);
+  e = cudaMemcpy(out_host, dev, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaFree(dev);
+  if (e != cudaSuccess) { note_cuda_error(e, "fast_div_selftest"); return FLOW3D_ERR_CUDA; }
+  return FLOW3D_OK;
+}
+
 }  // namespace f3d

@@ -8,13 +8,15 @@
 // (z-marching warps, vector loads, register-rotated z neighbours, shuffle x neighbours, per-level
 // precomputed image derivatives) is new.  A sensitivity study shows that merely changing
 // FMA contraction moves the final 128^3 flow by up to 9e-3 voxel, so this is what the 1e-3 gate needs.
+#include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <mutex>
+#include <string>
 #include <tuple>
 #include <vector>
 
-#include "common.cuh"
+#include "solve_args.cuh"
 
 namespace f3d {
 
@@ -88,24 +90,6 @@ __device__ __forceinline__ Vec<VEC> addv(const Vec<VEC>& a, const Vec<VEC>& b) {
 // ------------------------------------------------------------------------------------------------
 // Jacobi sweep
 // ------------------------------------------------------------------------------------------------
-struct SweepArgs {
-  const float *fx, *fy, *fz, *ft;
-  const float *u, *v, *w;
-  const float *du, *dv, *dw;
-  const float *phi, *ksi;
-  float *odu, *odv, *odw;
-  Dims g;
-  float hx, hy, hz, alpha;
-  int zchunk;
-  int pf;  // prefetch distance in planes (0 = off)
-  int zs, ze;  // compute range (local planes)
-  int lpr;     // lanes per row segment (32, 16 or 8)
-  int pf1;     // L1 prefetch of the next plane (0 = off)
-  int wx;      // warps side by side along x within a block
-  float* oksi; // KSI variant: the data-term weight is computed here (not read from `ksi`) and stored
-  float eps_d;
-};
-
 // Lane layout: a warp covers 32/lpr consecutive rows x (lpr*VEC) columns (lpr = lanes per row, a power
 // of two chosen per level so that ceil(w / (lpr*VEC)) tiles waste as few lanes as possible -- level
 // widths like 397 would otherwise leave a quarter of the lanes idle).
@@ -283,6 +267,8 @@ __device__ __forceinline__ void sweep_plane(const SweepArgs& a, const Dims& g, c
   const float wzm = (zg > 0) ? c.hz2 : 0.f;
 
   Vec<VEC> rdu, rdv, rdw;
+  // phase 1: everything up to the three dependent divisions, for the lane's VEC voxels
+  float numU[VEC], denU[VEC], denV[VEC], denW[VEC], sV[VEC], sW[VEC], j12[VEC], j13[VEC], j23[VEC], j24[VEC], j34[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     float wxp = c.hx2, wxm = c.hx2;
@@ -348,14 +334,37 @@ __device__ __forceinline__ void sweep_plane(const SweepArgs& a, const Dims& g, c
     }
     const float k = ks.v[i];
     const float ndu = __fmaf_rn(-J13, C.dw.v[i], __fmaf_rn(-J12, C.dv.v[i], -J14));
-    const float r_du = __fdiv_rn(__fmaf_rn(k, ndu, sumU), __fmaf_rn(J11, k, sumH));
-    const float ndv = __fmaf_rn(-J23, C.dw.v[i], __fmaf_rn(-J12, r_du, -J24));
-    const float r_dv = __fdiv_rn(__fmaf_rn(k, ndv, sumV), __fmaf_rn(J22, k, sumH));
-    const float ndw = __fmaf_rn(-J23, r_dv, __fmaf_rn(-J13, r_du, -J34));
-    const float r_dw = __fdiv_rn(__fmaf_rn(k, ndw, sumW), __fmaf_rn(J33, k, sumH));
-    rdu.v[i] = r_du;
-    rdv.v[i] = r_dv;
-    rdw.v[i] = r_dw;
+    numU[i] = __fmaf_rn(k, ndu, sumU);
+    denU[i] = __fmaf_rn(J11, k, sumH);
+    denV[i] = __fmaf_rn(J22, k, sumH);
+    denW[i] = __fmaf_rn(J33, k, sumH);
+    sV[i] = sumV; sW[i] = sumW;
+    j12[i] = J12; j13[i] = J13; j23[i] = J23; j24[i] = J24; j34[i] = J34;
+  }
+  // phase 2: du' -> dv' -> dw' (each needs the previous quotient) as three rounds over the VEC voxels,
+  // branch-free (common.cuh: div_fast), so the dependent chains of the voxels overlap
+  bool ok[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) { ok[i] = true; rdu.v[i] = div_fast(numU[i], denU[i], ok[i]); }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float ndv = __fmaf_rn(-j23[i], C.dw.v[i], __fmaf_rn(-j12[i], rdu.v[i], -j24[i]));
+    rdv.v[i] = div_fast(__fmaf_rn(ks.v[i], ndv, sV[i]), denV[i], ok[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float ndw = __fmaf_rn(-j23[i], rdv.v[i], __fmaf_rn(-j13[i], rdu.v[i], -j34[i]));
+    rdw.v[i] = div_fast(__fmaf_rn(ks.v[i], ndw, sW[i]), denW[i], ok[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    if (!ok[i]) {  // an operand outside the fast path's range (zero, tiny, huge, NaN): IEEE division
+      rdu.v[i] = __fdiv_rn(numU[i], denU[i]);
+      const float ndv = __fmaf_rn(-j23[i], C.dw.v[i], __fmaf_rn(-j12[i], rdu.v[i], -j24[i]));
+      rdv.v[i] = __fdiv_rn(__fmaf_rn(ks.v[i], ndv, sV[i]), denV[i]);
+      const float ndw = __fmaf_rn(-j23[i], rdv.v[i], __fmaf_rn(-j13[i], rdu.v[i], -j34[i]));
+      rdw.v[i] = __fdiv_rn(__fmaf_rn(ks.v[i], ndw, sW[i]), denW[i]);
+    }
   }
   if (c.active) {
     stv<VEC>(a.odu + oc, rdu);
@@ -522,37 +531,96 @@ static int pick_vec(const Dims& g) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Launch-shape autotuner.  The z-marching kernels give identical results for every vector width and
-// every z chunking, and which shape is fastest depends on the level size in ways a closed-form model
-// misses (wave quantisation at small levels, load balance across the two dies at large ones: measured,
-// profiles/).  So the first launch for a (kernel, w, h, depth) runs each candidate shape a few times on
-// the caller's own arguments (out != in, so repeating a launch is idempotent), times them with CUDA
-// events on the caller's stream and caches the winner; every later launch is a map lookup.
-// FLOW3D_AUTOTUNE=0 keeps the static heuristic.
+// Launch shapes.  Every vector width, z chunking and kernel variant (register-marching warps here, the
+// TMA-staged tiles of kernels_sweep_tma.cu) gives identical results, and which is fastest depends on the
+// level size in ways a closed-form model misses (wave quantisation at small levels, load balance across
+// the two dies at large ones: measured, profiles/).  Shapes therefore come from a per-device table:
+//   * launch_sweep / launch_phi_ksi only LOOK UP the table (never time, never synchronise: they are
+//     legal under stream capture and truly asynchronous); a missing entry means the static heuristic;
+//   * tune_level_kernels() -- reached through flow3d_solver_tune / flow3d_tune_kernels, both documented
+//     as synchronous -- times the candidates on scratch buffers and fills the table; its launches are
+//     not counted in flow3d_launch_count;
+//   * the table is persisted (FLOW3D_TUNE_CACHE or ~/.cache/flow3d_b200/) and reloaded per device.
+// FLOW3D_AUTOTUNE=0 ignores the table.
 // ------------------------------------------------------------------------------------------------
 struct TuneKey {
-  int kernel, w, h, ld, nzq;
+  int dev, kernel, w, h, ld, nzq;
   bool operator<(const TuneKey& o) const {
-    return std::tie(kernel, w, h, ld, nzq) < std::tie(o.kernel, o.w, o.h, o.ld, o.nzq);
+    return std::tie(dev, kernel, w, h, ld, nzq) < std::tie(o.dev, o.kernel, o.w, o.h, o.ld, o.nzq);
   }
 };
-struct TuneCfg {
-  int vec;
-  int nchunks;  // z chunks (0 = static heuristic)
-};
+enum { TK_SWEEP = 0, TK_PHI_KSI = 1, TK_SWEEP_KSI = 2, TK_PHI = 3 };
 static std::mutex g_tune_mu;
 static std::map<TuneKey, TuneCfg> g_tune;
+static unsigned long long g_tune_loaded = 0;  // bit per device: persisted table read
 
 static bool autotune_enabled() {
   static const int on = env_int("FLOW3D_AUTOTUNE", 1);
   return on != 0;
+}
+static int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+  return dev;
+}
+static std::string tune_cache_path(int dev) {
+  const char* e = getenv("FLOW3D_TUNE_CACHE");
+  if (e && *e) return std::string(e) == "off" ? std::string() : std::string(e);
+  const char* home = getenv("HOME");
+  if (!home || !*home) return std::string();
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { cudaGetLastError(); return std::string(); }
+  std::string name = prop.name;
+  for (char& c : name)
+    if (!((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || (c >= '0' && c <= '9'))) c = '_';
+  const std::string dir = std::string(home) + "/.cache/flow3d_b200";
+  const std::string cmd = "mkdir -p '" + dir + "' 2>/dev/null";
+  if (std::system(cmd.c_str()) != 0) return std::string();
+  return dir + "/tune_v2_" + name + "_" + std::to_string(prop.multiProcessorCount) + ".txt";
+}
+// g_tune_mu held
+static void tune_load_locked(int dev) {
+  if (dev < 0 || dev >= 64 || (g_tune_loaded & (1ull << dev))) return;
+  g_tune_loaded |= 1ull << dev;
+  const std::string path = tune_cache_path(dev);
+  if (path.empty()) return;
+  FILE* f = std::fopen(path.c_str(), "r");
+  if (!f) return;
+  TuneKey k;
+  TuneCfg c;
+  k.dev = dev;
+  while (std::fscanf(f, "%d %d %d %d %d %d %d %d", &k.kernel, &k.w, &k.h, &k.ld, &k.nzq, &c.vec, &c.nchunks,
+                     &c.variant) == 8) {
+    if ((c.vec == 1 || c.vec == 2 || c.vec == 4) && c.nchunks >= 0 && c.variant >= 0 && c.variant < SWEEP_VARIANT_COUNT)
+      g_tune.emplace(k, c);
+  }
+  std::fclose(f);
+}
+static void tune_store(const TuneKey& k, const TuneCfg& c) {
+  std::lock_guard<std::mutex> lk(g_tune_mu);
+  g_tune[k] = c;
+  const std::string path = tune_cache_path(k.dev);
+  if (path.empty()) return;
+  if (FILE* f = std::fopen(path.c_str(), "a")) {
+    std::fprintf(f, "%d %d %d %d %d %d %d %d\n", k.kernel, k.w, k.h, k.ld, k.nzq, c.vec, c.nchunks, c.variant);
+    std::fclose(f);
+  }
+}
+static bool tune_lookup(const TuneKey& k, TuneCfg* c) {
+  if (!autotune_enabled()) return false;
+  std::lock_guard<std::mutex> lk(g_tune_mu);
+  tune_load_locked(k.dev);
+  auto it = g_tune.find(k);
+  if (it == g_tune.end()) return false;
+  *c = it->second;
+  return true;
 }
 // whole-level launches are keyed by their exact depth; slab launches (ranges that shrink sweep by
 // sweep) share a key per 16 planes
 static TuneKey tune_key(int kernel, const Dims& g, ZRange zr) {
   const int nz = zr.end - zr.begin;
   const bool whole = zr.begin == 0 && zr.end == g.d && g.d == g.dg;
-  return TuneKey{kernel, g.w, g.h, g.ld, whole ? -nz : (nz + 15) / 16};
+  return TuneKey{current_device(), kernel, g.w, g.h, g.ld, whole ? -nz : (nz + 15) / 16};
 }
 static inline int chunk_len(int nz, int nchunks) {
   if (nchunks < 1) nchunks = 1;
@@ -569,9 +637,9 @@ static void chunk_candidates(int nz, long long per_plane, std::vector<int>& out)
   const int len0 = chunk_len(nz, (int)n0);
   int lens[16];
   int nl = 0;
-  const double f[] = {8.0, 4.0, 2.0, 1.333, 1.0, 0.667, 0.5, 0.333};
+  const double f[] = {4.0, 2.0, 1.333, 1.0, 0.667, 0.5};
   for (double k : f) lens[nl++] = (int)(len0 * k + 0.5);
-  const int small_lens[] = {2, 3, 4, 6, 8};
+  const int small_lens[] = {2, 4, 8};
   for (int l : small_lens)
     if (l < len0) lens[nl++] = l;
   out.clear();
@@ -584,35 +652,63 @@ static void chunk_candidates(int nz, long long per_plane, std::vector<int>& out)
     if (!dup) out.push_back(chunks);
   }
 }
+// Times every candidate on the caller's (scratch) arguments: out != in, so repeating a launch is
+// idempotent.  Two rounds of >= 4 back-to-back launches (>= ~2 ms) per candidate, minimum of the rounds.
+// SYNCHRONOUS; the launches are excluded from flow3d_launch_count.
 template <class Launch>
-static int tune_pick(const std::vector<TuneCfg>& cands, Launch&& launch, cudaStream_t st, TuneCfg* best) {
+static int tune_pick(const std::vector<TuneCfg>& cands, Launch&& launch, cudaStream_t st, TuneCfg* best,
+                     const char* what = "") {
+  if (cands.empty()) return FLOW3D_OK;
   cudaEvent_t e0, e1;
   if (cudaEventCreate(&e0) != cudaSuccess) return FLOW3D_ERR_CUDA;
   if (cudaEventCreate(&e1) != cudaSuccess) { cudaEventDestroy(e0); return FLOW3D_ERR_CUDA; }
-  // warm-up launch, timed: short kernels get more repetitions per candidate (>= ~1 ms of work each)
-  cudaEventRecord(e0, st);
-  int rc = launch(cands[0]);
-  cudaEventRecord(e1, st);
+  suppress_launch_count(true);
+  int rc = FLOW3D_OK;
+  auto timed = [&](const TuneCfg& c, int reps, float* ms) {
+    if (cudaEventRecord(e0, st) != cudaSuccess) return FLOW3D_ERR_CUDA;
+    for (int r = 0; r < reps; ++r) {
+      const int k = launch(c);
+      if (k != FLOW3D_OK) return k;
+    }
+    if (cudaEventRecord(e1, st) != cudaSuccess || cudaEventSynchronize(e1) != cudaSuccess ||
+        cudaEventElapsedTime(ms, e0, e1) != cudaSuccess)
+      return FLOW3D_ERR_CUDA;
+    return FLOW3D_OK;
+  };
   float warm_ms = 1.f;
-  if (cudaEventSynchronize(e1) == cudaSuccess) cudaEventElapsedTime(&warm_ms, e0, e1);
-  float best_ms = -1.f;
-  int reps = warm_ms > 0.f ? (int)(1.0f / warm_ms + 0.999f) : 3;
-  reps = reps < 3 ? 3 : (reps > 24 ? 24 : reps);
-  for (size_t i = 0; i < cands.size() && rc == FLOW3D_OK; ++i) {
-    cudaEventRecord(e0, st);
-    for (int r = 0; r < reps && rc == FLOW3D_OK; ++r) rc = launch(cands[i]);
-    cudaEventRecord(e1, st);
-    if (cudaEventSynchronize(e1) != cudaSuccess) { rc = FLOW3D_ERR_CUDA; break; }
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
-    if (best_ms < 0.f || ms < best_ms) { best_ms = ms; *best = cands[i]; }
+  rc = timed(cands[0], 1, &warm_ms);
+  int reps = warm_ms > 0.f ? (int)(2.0f / warm_ms + 0.999f) : 4;
+  reps = reps < 4 ? 4 : (reps > 40 ? 40 : reps);
+  std::vector<float> t(cands.size(), -1.f);
+  for (int round = 0; round < 2 && rc == FLOW3D_OK; ++round) {
+    for (size_t i = 0; i < cands.size() && rc == FLOW3D_OK; ++i) {
+      float ms = 0.f;
+      const int k = timed(cands[i], reps, &ms);
+      if (k == FLOW3D_ERR_UNSUPPORTED) continue;  // variant not usable for this level
+      rc = k;
+      if (rc == FLOW3D_OK && (t[i] < 0.f || ms < t[i])) t[i] = ms;
+    }
   }
+  float best_ms = -1.f;
+  for (size_t i = 0; i < cands.size(); ++i)
+    if (t[i] >= 0.f && (best_ms < 0.f || t[i] < best_ms)) { best_ms = t[i]; *best = cands[i]; }
+  static const int log = env_int("FLOW3D_TUNE_LOG", 0);
+  if (log) {  // per-candidate milliseconds per launch (stderr)
+    std::fprintf(stderr, "[flow3d tune] %s reps=%d:", what, reps);
+    for (size_t i = 0; i < cands.size(); ++i)
+      std::fprintf(stderr, " v%d/x%d/c%d=%.4f%s", cands[i].variant, cands[i].vec, cands[i].nchunks, t[i] / reps,
+                   (cands[i].variant == best->variant && cands[i].vec == best->vec && cands[i].nchunks == best->nchunks) ? "*" : "");
+    std::fprintf(stderr, "\n");
+  }
+  suppress_launch_count(false);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   return rc;
 }
 
 static int launch_sweep_cfg(SweepArgs a, const Dims& g, ZRange zr, TuneCfg cfg, cudaStream_t st) {
+  if (cfg.variant != SWEEP_VARIANT_REG)
+    return launch_sweep_tma(a, cfg.variant, cfg.nchunks > 0 ? chunk_len(zr.end - zr.begin, cfg.nchunks) : 0, st);
   const int vec = cfg.vec;
   static const int pf = env_int("FLOW3D_SWEEP_PF", 2);
   static const int rows = env_int("FLOW3D_SWEEP_ROWS", 4);
@@ -647,6 +743,53 @@ static int launch_sweep_cfg(SweepArgs a, const Dims& g, ZRange zr, TuneCfg cfg, 
   return check_launch("sweep_kernel");
 }
 
+// static choice for a level nobody tuned (FLOW3D_SWEEP_VARIANT forces a kernel variant: tests use it)
+static TuneCfg static_sweep_cfg(const Dims& g, ZRange zr) {
+  static const int forced_variant = env_int("FLOW3D_SWEEP_VARIANT", -1);
+  TuneCfg cfg{pick_vec(g), 0, SWEEP_VARIANT_REG};
+  int variant = forced_variant;
+  if (variant < 0) variant = SWEEP_VARIANT_REG;
+  if (variant != SWEEP_VARIANT_REG && sweep_tma_usable(g, variant)) {
+    cfg.variant = variant;
+    const int nz = zr.end - zr.begin;
+    cfg.nchunks = (nz + 31) / 32;  // ~32-plane chunks: prologue of 3 planes, enough CTAs to balance the SMs
+  }
+  return cfg;
+}
+
+static void sweep_candidates(const Dims& g, ZRange zr, std::vector<TuneCfg>& cands) {
+  const int nz = zr.end - zr.begin;
+  const int v0 = pick_vec(g);
+  int vecs[2] = {v0, 0};
+  if (v0 == 4) vecs[1] = 2;
+  else if (v0 == 2 && g.w >= 128) vecs[1] = 4;
+  else if (v0 == 2) vecs[1] = 1;  // narrow levels: more, thinner warps
+  std::vector<int> chunks;
+  for (int vi = 0; vi < 2; ++vi) {
+    const int vec = vecs[vi];
+    if (!vec) continue;
+    const int lpr = pick_lpr(g.w, vec);
+    const long long per_plane =
+        (long long)((g.w + lpr * vec - 1) / (lpr * vec)) * ((g.h + 4 * (32 / lpr) - 1) / (4 * (32 / lpr)));
+    chunk_candidates(nz, per_plane, chunks);
+    for (int c : chunks) cands.push_back(TuneCfg{vec, c, SWEEP_VARIANT_REG});
+  }
+  for (int variant = 1; variant < SWEEP_VARIANT_COUNT; ++variant) {
+    if (!sweep_tma_usable(g, variant) || g.w < 48 || g.h < 16 || nz < 16) continue;
+    const int lens[] = {32, 64, 128};
+    int seen[8], ns = 0;
+    for (int len : lens) {
+      if (len > nz) len = nz;
+      const int c = (nz + len - 1) / len;
+      bool dup = false;
+      for (int i = 0; i < ns; ++i) dup = dup || seen[i] == c;
+      if (dup) continue;
+      seen[ns++] = c;
+      cands.push_back(TuneCfg{4, c, variant});
+    }
+  }
+}
+
 int launch_sweep(const float* fx, const float* fy, const float* fz, const float* ft,
                  const float* u, const float* v, const float* w, const float* du, const float* dv,
                  const float* dw, const float* phi, const float* ksi, Dims g, ZRange zr, float hx,
@@ -655,39 +798,13 @@ int launch_sweep(const float* fx, const float* fy, const float* fz, const float*
   if (zr.end <= zr.begin) return FLOW3D_OK;
   SweepArgs a{fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, odu, odv, odw, g, hx, hy, hz, alpha, 0, 0,
               zr.begin, zr.end, 32, 0, 1, ksi_out, eps_d};
-  const int nz = zr.end - zr.begin;
-  TuneCfg cfg{pick_vec(g), 0};
-  static const int forced_vec = env_int("FLOW3D_SWEEP_VEC", 0);
-  if (autotune_enabled() && forced_vec == 0 && nz >= 4) {
-    const TuneKey key = tune_key(ksi_out ? 2 : 0, g, zr);
-    bool have;
-    {
-      std::lock_guard<std::mutex> lk(g_tune_mu);
-      auto it = g_tune.find(key);
-      have = it != g_tune.end();
-      if (have) cfg = it->second;
-    }
-    if (!have) {
-      std::vector<TuneCfg> cands;
-      std::vector<int> chunks;
-      int vecs[2] = {cfg.vec, 0};
-      if (cfg.vec == 4) vecs[1] = 2;
-      else if (cfg.vec == 2 && g.w >= 128) vecs[1] = 4;
-      else if (cfg.vec == 2) vecs[1] = 1;  // narrow levels: more, thinner warps
-      for (int vi = 0; vi < 2; ++vi) {
-        const int vec = vecs[vi];
-        if (!vec) continue;
-        const int lpr = pick_lpr(g.w, vec);
-        const long long per_plane = (long long)((g.w + lpr * vec - 1) / (lpr * vec)) * ((g.h + 4 * (32 / lpr) - 1) / (4 * (32 / lpr)));
-        chunk_candidates(nz, per_plane, chunks);
-        for (int c : chunks) cands.push_back(TuneCfg{vec, c});
-      }
-      F3D_TRY_RC(tune_pick(cands, [&](TuneCfg c) { return launch_sweep_cfg(a, g, zr, c, st); }, st, &cfg));
-      std::lock_guard<std::mutex> lk(g_tune_mu);
-      g_tune[key] = cfg;
-    }
-  }
-  return launch_sweep_cfg(a, g, zr, cfg, st);
+  TuneCfg cfg = static_sweep_cfg(g, zr);
+  static const int forced_vec = env_int("FLOW3D_SWEEP_VEC", 0), forced_variant = env_int("FLOW3D_SWEEP_VARIANT", -1);
+  if (forced_vec == 0 && forced_variant < 0) tune_lookup(tune_key(ksi_out ? TK_SWEEP_KSI : TK_SWEEP, g, zr), &cfg);
+  const int rc = launch_sweep_cfg(a, g, zr, cfg, st);
+  if (rc == FLOW3D_ERR_UNSUPPORTED && cfg.variant != SWEEP_VARIANT_REG)  // no TMA entry point in this driver
+    return launch_sweep_cfg(a, g, zr, TuneCfg{pick_vec(g), 0, SWEEP_VARIANT_REG}, st);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -896,6 +1013,27 @@ static int launch_phi_ksi_cfg(const PhiKsiArgs& a, const Dims& g, ZRange zr, Tun
   return check_launch("phi_ksi_kernel");
 }
 
+// one sweep with an explicit launch shape (tests, scripts): FLOW3D_ERR_UNSUPPORTED if the variant cannot
+// run this level
+int launch_sweep_shape(const float* fx, const float* fy, const float* fz, const float* ft, const float* u,
+                       const float* v, const float* w, const float* du, const float* dv, const float* dw,
+                       const float* phi, const float* ksi, Dims g, ZRange zr, float hx, float hy, float hz,
+                       float alpha, float* odu, float* odv, float* odw, cudaStream_t st, float* ksi_out, float eps_d,
+                       int variant, int vec, int nchunks) {
+  if (zr.end <= zr.begin) return FLOW3D_OK;
+  if (variant < 0 || variant >= SWEEP_VARIANT_COUNT || !(vec == 1 || vec == 2 || vec == 4) || nchunks < 0)
+    return FLOW3D_ERR_INVALID_ARG;
+  SweepArgs a{fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, odu, odv, odw, g, hx, hy, hz, alpha, 0, 0,
+              zr.begin, zr.end, 32, 0, 1, ksi_out, eps_d};
+  return launch_sweep_cfg(a, g, zr, TuneCfg{vec, nchunks, variant}, st);
+}
+
+static int static_phi_vec(const Dims& g) {
+  static const int forced = env_int("FLOW3D_PHIKSI_VEC", 0);
+  if (forced == 1 || forced == 2 || forced == 4) return forced;
+  return (g.w >= 48) ? 2 : 1;  // measured: VEC=2 (16+ warps/SM) beats VEC=4 (191 regs)
+}
+
 int launch_phi_ksi(const float* fx, const float* fy, const float* fz, const float* ft,
                    const float* u, const float* v, const float* w, const float* du,
                    const float* dv, const float* dw, Dims g, ZRange zr, float hx, float hy, float hz,
@@ -903,37 +1041,84 @@ int launch_phi_ksi(const float* fx, const float* fy, const float* fz, const floa
   if (zr.end <= zr.begin) return FLOW3D_OK;
   PhiKsiArgs a{fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, g, hx, hy, hz, eps_s, eps_d};
   static const int forced = env_int("FLOW3D_PHIKSI_VEC", 0);
-  int vec = (g.w >= 48) ? 2 : 1;  // measured: VEC=2 (16+ warps/SM) beats VEC=4 (191 regs)
-  if (forced == 1 || forced == 2 || forced == 4) vec = forced;
-  TuneCfg cfg{vec, 0};
-  const int nz = zr.end - zr.begin;
-  if (autotune_enabled() && forced == 0 && nz >= 4) {
-    const TuneKey key = tune_key(ksi ? 1 : 3, g, zr);
-    bool have;
-    {
-      std::lock_guard<std::mutex> lk(g_tune_mu);
-      auto it = g_tune.find(key);
-      have = it != g_tune.end();
-      if (have) cfg = it->second;
-    }
-    if (!have) {
-      std::vector<TuneCfg> cands;
-      std::vector<int> chunks;
-      int vecs[2] = {vec, (vec == 2 && g.w >= 128) ? 4 : 0};
-      for (int vi = 0; vi < 2; ++vi) {
-        const int vc = vecs[vi];
-        if (!vc) continue;
-        const int lpr = pick_lpr(g.w, vc);
-        const long long per_plane = (long long)((g.w + lpr * vc - 1) / (lpr * vc)) * ((g.h + 4 * (32 / lpr) - 1) / (4 * (32 / lpr)));
-        chunk_candidates(nz, per_plane, chunks);
-        for (int c : chunks) cands.push_back(TuneCfg{vc, c});
-      }
-      F3D_TRY_RC(tune_pick(cands, [&](TuneCfg c) { return launch_phi_ksi_cfg(a, g, zr, c, st); }, st, &cfg));
-      std::lock_guard<std::mutex> lk(g_tune_mu);
-      g_tune[key] = cfg;
-    }
-  }
+  TuneCfg cfg{static_phi_vec(g), 0, 0};
+  if (forced == 0) tune_lookup(tune_key(ksi ? TK_PHI_KSI : TK_PHI, g, zr), &cfg);
   return launch_phi_ksi_cfg(a, g, zr, cfg, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// explicit tuning of one level's solver kernels (SYNCHRONOUS).  `bufs`: 16 scratch volumes of the level's
+// size; they are filled with a finite positive pattern (0x3f3f3f3f = 0.747) so that no candidate runs
+// through denormal / NaN slow paths.
+// ------------------------------------------------------------------------------------------------
+int tune_level_kernels(Dims g, ZRange zr, float* const bufs[16], float hx, float hy, float hz, cudaStream_t st) {
+  if (!autotune_enabled()) return FLOW3D_OK;
+  const int nz = zr.end - zr.begin;
+  if (nz < 4) return FLOW3D_OK;
+  const TuneKey k_sweep = tune_key(TK_SWEEP, g, zr), k_ksi = tune_key(TK_SWEEP_KSI, g, zr),
+                k_phi = tune_key(TK_PHI, g, zr);
+  TuneCfg tmp;
+  const bool have_sweep = tune_lookup(k_sweep, &tmp), have_ksi = tune_lookup(k_ksi, &tmp),
+             have_phi = tune_lookup(k_phi, &tmp);
+  if (have_sweep && have_ksi && have_phi) return FLOW3D_OK;
+  const size_t bytes = (size_t)g.ps * g.d * sizeof(float);
+  for (int i = 0; i < 16; ++i)
+    if (cudaMemsetAsync(bufs[i], 0x3f, bytes, st) != cudaSuccess) { cudaGetLastError(); return FLOW3D_ERR_CUDA; }
+  const float alpha = 7.5f, eps = 0.001f;
+  SweepArgs a{bufs[0], bufs[1], bufs[2], bufs[3], bufs[4], bufs[5], bufs[6], bufs[7], bufs[8], bufs[9], bufs[10],
+              bufs[11], bufs[12], bufs[13], bufs[14], g, hx, hy, hz, alpha, 0, 0, zr.begin, zr.end, 32, 0, 1,
+              nullptr, eps};
+  std::vector<TuneCfg> cands;
+  TuneCfg best;
+  char lbl[96];
+  auto label = [&](const char* k) {
+    std::snprintf(lbl, sizeof(lbl), "%s %dx%dx%d[%d,%d)", k, g.w, g.h, g.d, zr.begin, zr.end);
+    return (const char*)lbl;
+  };
+  if (!have_sweep) {
+    sweep_candidates(g, zr, cands);
+    best = static_sweep_cfg(g, zr);
+    F3D_TRY_RC(tune_pick(cands, [&](TuneCfg c) { return launch_sweep_cfg(a, g, zr, c, st); }, st, &best, label("sweep")));
+    tune_store(k_sweep, best);
+  }
+  if (!have_ksi) {
+    SweepArgs ak = a;
+    ak.oksi = bufs[15];
+    cands.clear();
+    sweep_candidates(g, zr, cands);
+    best = static_sweep_cfg(g, zr);
+    F3D_TRY_RC(tune_pick(cands, [&](TuneCfg c) { return launch_sweep_cfg(ak, g, zr, c, st); }, st, &best, label("sweep+ksi")));
+    tune_store(k_ksi, best);
+  }
+  if (!have_phi) {
+    PhiKsiArgs pa{bufs[0], bufs[1], bufs[2], bufs[3], bufs[4], bufs[5], bufs[6], bufs[7], bufs[8], bufs[9], bufs[10],
+                  nullptr, g, hx, hy, hz, eps, eps};
+    cands.clear();
+    const int v0 = static_phi_vec(g);
+    int vecs[2] = {v0, (v0 == 2 && g.w >= 128) ? 4 : 0};
+    std::vector<int> chunks;
+    for (int vi = 0; vi < 2; ++vi) {
+      const int vc = vecs[vi];
+      if (!vc) continue;
+      const int lpr = pick_lpr(g.w, vc);
+      const long long per_plane =
+          (long long)((g.w + lpr * vc - 1) / (lpr * vc)) * ((g.h + 4 * (32 / lpr) - 1) / (4 * (32 / lpr)));
+      chunk_candidates(nz, per_plane, chunks);
+      for (int c : chunks) cands.push_back(TuneCfg{vc, c, 0});
+    }
+    best = TuneCfg{v0, 0, 0};
+    F3D_TRY_RC(tune_pick(cands, [&](TuneCfg c) { return launch_phi_ksi_cfg(pa, g, zr, c, st); }, st, &best, label("phi")));
+    tune_store(k_phi, best);
+  }
+  return FLOW3D_OK;
+}
+
+// read-only view of the table (tests, scripts/level_table.py)
+int tune_query(int kernel, Dims g, ZRange zr, int out[3]) {
+  TuneCfg c;
+  if (!tune_lookup(tune_key(kernel, g, zr), &c)) return 0;
+  out[0] = c.vec; out[1] = c.nchunks; out[2] = c.variant;
+  return 1;
 }
 
 // ------------------------------------------------------------------------------------------------

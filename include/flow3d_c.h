@@ -201,6 +201,18 @@ int flow3d_warp_derivatives_slab(const float* f0, const float* f1, size_t f1_z0_
                                  const float* w, const size_t dims[3], size_t ld,
                                  const flow3d_zslab* slab, const float h[3], float* fx, float* fy,
                                  float* fz, float* ft, void* stream);
+/* One Jacobi sweep with an explicit launch shape (tests and tuning scripts; production launches take the
+ * shape from the tuning table): variant 0 = register-marching warps (vec = voxels per lane 1/2/4), 1 / 2 =
+ * TMA-staged 64x8 / 32x16 tiles; nchunks = z chunks (0 = default).  ksi_out != NULL: the sweep computes
+ * the data-term weight from the iterate it reads (first sweep of an outer iteration), stores it there and
+ * ignores `ksi`.  slab may be NULL (whole volume).  Every shape gives identical bits.
+ * FLOW3D_ERR_UNSUPPORTED when the variant cannot run this level. */
+int flow3d_sweep_shape(const float* fx, const float* fy, const float* fz, const float* ft, const float* u,
+                       const float* v, const float* w, const float* du, const float* dv, const float* dw,
+                       const float* phi, const float* ksi, const size_t dims[3], size_t ld,
+                       const flow3d_zslab* slab, const float h[3], float alpha, float eps_data, float* du_out,
+                       float* dv_out, float* dw_out, float* ksi_out, int variant, int vec, int nchunks,
+                       void* stream);
 /* One outer iteration on a z-slab in ONE call: phi/ksi on the slab's [z_begin, z_end), then `inner`
  * Jacobi sweeps on ranges that shrink by one plane per sweep on every side that is NOT a global face
  * (sweep j computes [z_begin + j, z_end - j) there), ping-ponging between (du,dv,dw) and (tdu,tdv,tdw).
@@ -246,6 +258,21 @@ int flow3d_solver_compute_host(flow3d_solver* s, const float* frame_0, const flo
 int flow3d_solver_compute_device(flow3d_solver* s, const float* frame_0, const float* frame_1,
                                  size_t ld, const flow3d_params* params, float* flow_u,
                                  float* flow_v, float* flow_w, void* stream);
+
+/* ---- launch shapes ---------------------------------------------------------------------------------
+ * The solver kernels (Jacobi sweep, phi) exist in several launch shapes / variants that give identical
+ * bits; which one is fastest depends on the level size.  Launches only LOOK UP a per-device table (a
+ * missing entry = static heuristic), so flow3d_solver_compute_device and the stage calls stay
+ * asynchronous and capturable.  These calls fill the table; they time candidates with CUDA events and
+ * are SYNCHRONOUS.  The table is persisted in $FLOW3D_TUNE_CACHE (default ~/.cache/flow3d_b200/, "off"
+ * disables); FLOW3D_AUTOTUNE=0 ignores it.  flow3d_solver_compute_host tunes on first use.
+ * flow3d_tune_kernels: scratch = 16 volumes of the slab's size (contents destroyed). */
+int flow3d_solver_tune(flow3d_solver* s, const flow3d_params* params);
+int flow3d_tune_kernels(const size_t dims[3], size_t ld, const flow3d_zslab* slab, const float h[3],
+                        float* scratch, size_t scratch_floats, void* stream);
+/* table entry of kernel 0 = sweep, 1 = phi+ksi, 2 = sweep computing ksi, 3 = phi: returns 1 and
+ * out = {voxels per lane, z chunks, variant (0 register-marching, 1/2 TMA tiles 64x8 / 32x16)}, 0 if none */
+int flow3d_tune_query(int kernel, const size_t dims[3], size_t ld, const flow3d_zslab* slab, int out[3]);
 
 /* milliseconds of the last compute call, measured with CUDA events: [0] whole call (host call:
  * including H2D/D2H, the reference's own bracket optical_flow_e.cpp:169->579), [1] device-only */
@@ -294,6 +321,14 @@ int flow3d_solver_set_diagnostics(flow3d_solver* s, int enable, float update_tol
  * Arrays may be NULL; at most `capacity` entries are written to each. */
 int flow3d_solver_diagnostics(flow3d_solver* s, size_t* n_levels, size_t* outer_per_level, double* rms,
                               double* max_abs, size_t capacity, size_t* n_records);
+
+/* ---- self-test ------------------------------------------------------------------------------------
+ * The sweep kernels divide with the branch-free fast path of div.rn.f32 (csrc/common.cuh: div_fast) and
+ * fall back to the IEEE division for operands outside [2^-60, 2^60].  This runs n_pairs divisions on the
+ * device both ways: mode 0 = random operands, mode 1 = every divisor mantissa (n_pairs = k * 2^23).
+ * out[0] = quotients that differ from IEEE division (must be 0), out[1] = pairs sent to the fallback,
+ * out[2] = pairs tested.  Synchronous. */
+int flow3d_selftest_fast_div(uint64_t n_pairs, uint64_t seed, int mode, uint64_t out[3]);
 
 /* ---- synthetic test volumes ---------------------------------
  * Analytic texture pair with a known rigid motion, generated on the device in double precision.

@@ -32,6 +32,25 @@ def _stage(guarded):
     return os.path.join(dst, "flow3d_ref")
 
 
+def run_reference_files(p0, p1, dims, reps=1, out_prefix=None, params=None, guarded=False, u8=False,
+                        timeout=3600):
+    """Run the reference build on two RAW files already on disk (dims = (W, H, D)).  Returns
+    ([seconds per rep], stdout); the flows are written to <out_prefix>_{u,v,w}.raw when a prefix is given.
+    Nothing of this repository's own library is involved: the process started here is oracle/_ref/flow3d_ref."""
+    if not available():
+        raise RuntimeError("oracle/_ref not built (run oracle/build_ref.sh where /root/reference exists)")
+    exe = _stage(guarded)
+    w, h, d = dims
+    cmd = [exe, p0, p1, str(w), str(h), str(d), "u8" if u8 else "f32", out_prefix or "-", str(reps)]
+    for k, v in (params or {}).items():
+        cmd.append("%s=%s" % (k, v))
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("reference run failed (%d):\n%s" % (res.returncode, res.stdout[-2000:]))
+    times = [float(x) for x in re.findall(r"REF_SOLVE rep=\d+ seconds=([0-9.]+)", res.stdout)]
+    return times, res.stdout
+
+
 def run_reference(f0, f1, params=None, reps=1, guarded=False, u8=False, want_output=True, timeout=3600,
                   workdir=None):
     """f0, f1: numpy (D,H,W) volumes.  Returns (u, v, w, [seconds per rep], stdout)."""

@@ -22,6 +22,10 @@ ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--alias-f", action="store_true", help="experiment: pass fx/fy also as fz/ft (13 distinct words)")
 ap.add_argument("--alias-most", action="store_true", help="experiment: one buffer for all nine static fields (7 distinct words)")
 ap.add_argument("--ld-align", type=int, default=0, help="override the row pitch alignment (floats)")
+ap.add_argument("--variant", type=int, default=-1, help="sweep: explicit kernel variant (0 register, 1/2 TMA tiles)")
+ap.add_argument("--vec", type=int, default=4)
+ap.add_argument("--nchunks", type=int, default=0)
+ap.add_argument("--ksi", action="store_true", help="sweep: the variant that also computes ksi")
 args = ap.parse_args()
 L = pkg.load()
 pkg.require_device()
@@ -58,6 +62,11 @@ o = [torch.empty(n, device="cuda") for _ in range(4)]
 
 
 def run():
+    if args.stage == "sweep" and args.variant >= 0:
+        check(L.flow3d_sweep_shape(P(fx), P(fy), P(fz), P(ft), P(u), P(v), P(w), P(du), P(dv), P(dw), P(phi), P(ksi),
+                                   dims, ld, None, h, 7.5, 0.001, P(o[0]), P(o[1]), P(o[2]), P(o[3]) if args.ksi else None,
+                                   args.variant, args.vec, args.nchunks, sp), "sweep_shape")
+        return 52.0
     if args.stage == "sweep":
         if args.alias_most:
             check(L.flow3d_sweep(P(phi), P(phi), P(phi), P(phi), P(phi), P(phi), P(phi), P(du), P(dv), P(dw), P(phi), P(phi),
@@ -81,6 +90,9 @@ def run():
         check(L.flow3d_warp_derivatives(P(fx), P(fy), P(u), P(v), P(w), dims, ld, h, P(o[0]), P(o[1]), P(o[2]),
                                         P(o[3]), sp), "warp")
         return 36.0
+    if args.stage == "blur":
+        check(L.flow3d_gauss_blur(P(u), P(o[0]), P(o[1]), dims, ld, 2.0, sp), "blur")
+        return 24.0
     if args.stage == "resample":
         od = sz3((int(W * 0.95), int(H * 0.95), int(D * 0.95)))
         check(L.flow3d_resample(P(u), dims, ld, P(o[0]), od, int(L.flow3d_aligned_ld(int(W * 0.95))), P(o[1]), P(o[2]),
