@@ -707,7 +707,7 @@ static int tune_pick(const std::vector<TuneCfg>& cands, Launch&& launch, cudaStr
 }
 
 static int launch_sweep_cfg(SweepArgs a, const Dims& g, ZRange zr, TuneCfg cfg, cudaStream_t st) {
-  if (cfg.variant != SWEEP_VARIANT_REG)
+  if (sweep_variant_is_tma(cfg.variant))
     return launch_sweep_tma(a, cfg.variant, cfg.nchunks > 0 ? chunk_len(zr.end - zr.begin, cfg.nchunks) : 0, st);
   const int vec = cfg.vec;
   static const int pf = env_int("FLOW3D_SWEEP_PF", 2);
@@ -749,7 +749,7 @@ static TuneCfg static_sweep_cfg(const Dims& g, ZRange zr) {
   TuneCfg cfg{pick_vec(g), 0, SWEEP_VARIANT_REG};
   int variant = forced_variant;
   if (variant < 0) variant = SWEEP_VARIANT_REG;
-  if (variant != SWEEP_VARIANT_REG && sweep_tma_usable(g, variant)) {
+  if (sweep_variant_is_tma(variant) && sweep_tma_usable(g, variant)) {
     cfg.variant = variant;
     const int nz = zr.end - zr.begin;
     cfg.nchunks = (nz + 31) / 32;  // ~32-plane chunks: prologue of 3 planes, enough CTAs to balance the SMs
@@ -774,9 +774,13 @@ static void sweep_candidates(const Dims& g, ZRange zr, std::vector<TuneCfg>& can
     chunk_candidates(nz, per_plane, chunks);
     for (int c : chunks) cands.push_back(TuneCfg{vec, c, SWEEP_VARIANT_REG});
   }
-  for (int variant = 1; variant < SWEEP_VARIANT_COUNT; ++variant) {
-    if (!sweep_tma_usable(g, variant) || g.w < 48 || g.h < 16 || nz < 16) continue;
-    const int lens[] = {32, 64, 128};
+  // The TMA-staged tile kernel (kernels_sweep_tma.cu) is a candidate only on request: measured on B200 it
+  // trails the register kernel on every level (512^3: 1.42 ms vs 1.34 ms), so timing it
+  // only lengthens the tuning pass.  FLOW3D_TUNE_TMA=1 adds it.
+  static const int tune_tma = env_int("FLOW3D_TUNE_TMA", 0);
+  for (int variant = 1; tune_tma && variant < SWEEP_VARIANT_COUNT; ++variant) {
+    if (!sweep_variant_is_tma(variant) || !sweep_tma_usable(g, variant) || g.w < 128 || g.h < 32 || nz < 32) continue;
+    const int lens[] = {64, 128};
     int seen[8], ns = 0;
     for (int len : lens) {
       if (len > nz) len = nz;
@@ -802,7 +806,7 @@ int launch_sweep(const float* fx, const float* fy, const float* fz, const float*
   static const int forced_vec = env_int("FLOW3D_SWEEP_VEC", 0), forced_variant = env_int("FLOW3D_SWEEP_VARIANT", -1);
   if (forced_vec == 0 && forced_variant < 0) tune_lookup(tune_key(ksi_out ? TK_SWEEP_KSI : TK_SWEEP, g, zr), &cfg);
   const int rc = launch_sweep_cfg(a, g, zr, cfg, st);
-  if (rc == FLOW3D_ERR_UNSUPPORTED && cfg.variant != SWEEP_VARIANT_REG)  // no TMA entry point in this driver
+  if (rc == FLOW3D_ERR_UNSUPPORTED && sweep_variant_is_tma(cfg.variant))  // no TMA entry point in this driver
     return launch_sweep_cfg(a, g, zr, TuneCfg{pick_vec(g), 0, SWEEP_VARIANT_REG}, st);
   return rc;
 }

@@ -75,11 +75,7 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar)
       : "memory");
 }
-// TMA prefetch of one box into L2 (no shared-memory destination, no barrier)
-__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* map, int x, int y, int z) {
-  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(x), "r"(y), "r"(z)
-               : "memory");
-}
+__device__ __forceinline__ void prefetch_l2(const float* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -126,37 +122,52 @@ __device__ __forceinline__ float comp(const float4& v, int i) { return i == 0 ? 
 
 // x-1 / x+1 neighbours of a thread's four voxels: inside the float4, from the adjacent lanes of the same
 // tile row (shuffle) and, for the first / last lane of a row, from the halo columns in shared memory.
-// EDGE: at the volume faces the reflect-101 neighbour is substituted (x = 0 -> value at 1, x = w-1 ->
-// value at w-2), what the reference's shared-memory halo holds (solve_3d.cu:326-355).
-template <bool EDGE, int LX>
-__device__ __forceinline__ void x_nb(const float4& c, const float* row_c, int lx, int gx0, int w, float (&l)[4],
-                                     float (&r)[4]) {
+// At the volume faces the reflect-101 neighbour is substituted (x = 0 -> value at 1, x = w-1 -> value at
+// w-2), what the reference's shared-memory halo holds (solve_3d.cu:326-355).  One code path serves every
+// tile (a two-variant build stalled on instruction fetch), and the faces cost almost nothing in it:
+//   * x = 0 can only be element 0 of a row's first lane: it takes c.y instead of the halo (face_lo);
+//   * x = w-1 as element 3 takes c.z instead of its right neighbour (face_hi3);
+//   * x = w-1 as element i < 3 (w not a multiple of 4) is handled where the vector is LOADED, by
+//     mirror_tail(): element i+1 (column w, out of the volume, TMA zero fill) is overwritten with element
+//     i-1, so the plain in-vector neighbour is already the mirrored one.
+template <int LX>
+__device__ __forceinline__ void x_nb(const float4& c, const float* row_c, int lx, bool face_lo, bool face_hi3,
+                                     float (&l)[4], float (&r)[4]) {
   float from_left = __shfl_up_sync(0xffffffffu, c.w, 1);
   float from_right = __shfl_down_sync(0xffffffffu, c.x, 1);
   if (lx == 0) from_left = row_c[-1];
   if (lx == LX - 1) from_right = row_c[4];
-  const float v[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float a = (i > 0) ? v[i - 1] : from_left;
-    const float b = (i < 3) ? v[i + 1] : from_right;
-    if constexpr (EDGE) {
-      const int x = gx0 + i;
-      l[i] = (x == 0) ? b : a;
-      r[i] = (x == w - 1) ? a : b;
-    } else {
-      l[i] = a;
-      r[i] = b;
-    }
-  }
+  if (face_lo) from_left = c.y;
+  if (face_hi3) from_right = c.z;
+  l[0] = from_left; l[1] = c.x; l[2] = c.y; l[3] = c.z;
+  r[0] = c.y; r[1] = c.z; r[2] = c.w; r[3] = from_right;
+}
+// tail = index (1..3) of the first out-of-volume element of a vector that holds x = w-1 as element
+// tail-1 < 3, else 0: that element receives the mirror neighbour of x = w-1 (element tail-2; for tail = 1
+// that is the previous lane's last element, which the caller passes as `left`)
+__device__ __forceinline__ void mirror_tail(float4& c, int tail, float left) {
+  if (tail == 1) c.y = left;
+  else if (tail == 2) c.z = c.x;
+  else if (tail == 3) c.w = c.y;
+}
+
+// IEEE-division recomputation of one voxel whose operands left div_fast's range (kept out of line: rare,
+// and the hot loop must stay small)
+__device__ __noinline__ float3 slow_voxel(float numU, float denU, float denV, float denW, float k, float sV, float sW,
+                                          float j12, float j13, float j23, float j24, float j34, float dw) {
+  const float du = __fdiv_rn(numU, denU);
+  const float ndv = __fmaf_rn(-j23, dw, __fmaf_rn(-j12, du, -j24));
+  const float dv = __fdiv_rn(__fmaf_rn(k, ndv, sV), denV);
+  const float ndw = __fmaf_rn(-j23, dv, __fmaf_rn(-j13, du, -j34));
+  return make_float3(du, dv, __fdiv_rn(__fmaf_rn(k, ndw, sW), denW));
 }
 
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int kPrefetchAhead = 4;  // planes between the L2 prefetch of a box and its first use
+constexpr int kPf = 3;  // planes between a thread's L2 prefetch and the TMA copy of that plane
 
-template <int BX, int BY, bool KSI, bool EDGE>
+template <int BX, int BY, bool KSI>
 __device__ __forceinline__ void sweep_tma_run(const TmaMaps& maps, const SweepArgs& a, unsigned char* smem) {
   using L = TL<BX, BY, KSI>;
   const Dims g = a.g;
@@ -180,7 +191,7 @@ __device__ __forceinline__ void sweep_tma_run(const TmaMaps& maps, const SweepAr
     const uint32_t bar = barA + 8 * s;
     mbar_expect_tx(bar, 6 * L::HBOX);
     const int z = zplane(q);
-#pragma unroll
+#pragma unroll 1
     for (int f = 0; f < 3; ++f) {
       tma_load_3d(sbase + L::OFF_U + (s * 3 + f) * L::HP, &maps.m[M_U + f], tx0 - 4, ty0 - 1, z, bar);
       tma_load_3d(sbase + L::OFF_S + (s * 3 + f) * L::HP, &maps.m[M_DU + f], tx0 - 4, ty0 - 1, z, bar);
@@ -197,21 +208,9 @@ __device__ __forceinline__ void sweep_tma_run(const TmaMaps& maps, const SweepAr
     const uint32_t bar = barC + 8 * s;
     mbar_expect_tx(bar, L::NC * L::CP);
     const int z = zb + q;
-#pragma unroll
+#pragma unroll 1
     for (int f = 0; f < L::NC; ++f)
       tma_load_3d(sbase + L::OFF_C + (s * L::NC + f) * L::CP, &maps.m[M_FX + f], tx0, ty0, z, bar);
-  };
-  // L2 prefetch of every box of plane q: the shallow rings B and C are filled only one step before their
-  // first use (shared memory is spent on the deep ring A), so their copies must be L2 hits
-  auto prefetch_plane = [&](int q) {
-    if (q > n) return;
-    const int z = zplane(q);
-#pragma unroll
-    for (int f = 0; f < 7; ++f) tma_prefetch_l2_3d(&maps.m[M_U + f], tx0 - 4, ty0 - 1, z);
-    if (q <= n - 1) {
-#pragma unroll
-      for (int f = 0; f < L::NC; ++f) tma_prefetch_l2_3d(&maps.m[M_FX + f], tx0, ty0, zb + q);
-    }
   };
   auto waitA = [&](int q) { const int k = q + 1; mbar_wait(barA + 8 * (k & 3), (k >> 2) & 1); };
   auto waitB = [&](int q) { const int k = q + 1; mbar_wait(barB + 8 * (k % 3), (k / 3) & 1); };
@@ -224,23 +223,34 @@ __device__ __forceinline__ void sweep_tma_run(const TmaMaps& maps, const SweepAr
   float* const fD = reinterpret_cast<float*>(smem + L::OFF_D);
   constexpr int HPf = L::HP / 4, CPf = L::CP / 4;
 
-  // S = u + du etc. of plane q in place, over the whole haloed box; raw increments of the tile to ring D
+  // S = u + du etc. of plane q in place, over the whole haloed box; raw increments of the tile to ring D.
+  // Thread t handles the float4 cells t, t + CONSUMERS, ...: their offsets are loop invariants.
+  constexpr int NCELL = L::HX4 * L::HY;
+  constexpr int PRE_ITERS = (NCELL + L::CONSUMERS - 1) / L::CONSUMERS;
+  int pre_off[PRE_ITERS], pre_coff[PRE_ITERS];  // pre_coff < 0: not a tile cell (halo) or no cell
+#pragma unroll
+  for (int it = 0; it < PRE_ITERS; ++it) {
+    const int i = tid + it * L::CONSUMERS;
+    const int r = i / L::HX4, c = i - r * L::HX4;
+    pre_off[it] = (i < NCELL) ? r * L::HX + 4 * c : -1;
+    const bool inner = (i < NCELL) && (r >= 1) && (r <= BY) && (c >= 1) && (c <= L::LX);
+    pre_coff[it] = inner ? (r - 1) * BX + 4 * (c - 1) : -1;
+  }
   auto prepass = [&](int q) {
     const int k = q + 1, sa = k & 3, sd = k % 3;
     float* S0 = fS + (sa * 3) * HPf;
     const float* U0 = fU + (sa * 3) * HPf;
     float* D0 = fD + (sd * L::ND) * CPf;
-    for (int i = tid; i < L::HX4 * L::HY; i += L::CONSUMERS) {
-      const int r = i / L::HX4, c = i - r * L::HX4;
-      const int off = r * L::HX + 4 * c;
-      const bool inner = (r >= 1) && (r <= BY) && (c >= 1) && (c <= L::LX);
-      const int coff = (r - 1) * BX + 4 * (c - 1);
+#pragma unroll
+    for (int it = 0; it < PRE_ITERS; ++it) {
+      const int off = pre_off[it], coff = pre_coff[it];
+      if (off < 0) continue;
 #pragma unroll
       for (int f = 0; f < 3; ++f) {
         const float4 d = ld4(S0 + f * HPf + off);
         const float4 uu = ld4(U0 + f * HPf + off);
         st4(S0 + f * HPf + off, add4(uu, d));
-        if (inner) {
+        if (coff >= 0) {
           if constexpr (KSI) st4(D0 + f * CPf + coff, d);
           else if (f > 0) st4(D0 + (f - 1) * CPf + coff, d);
         }
@@ -263,11 +273,12 @@ __device__ __forceinline__ void sweep_tma_run(const TmaMaps& maps, const SweepAr
 #pragma unroll 1
       for (int i = 0; i < M_COUNT; ++i)
         if (!(KSI && i == M_KSI)) tma_prefetch_desc(&maps.m[i]);
-      issueA(-1); issueB(-1);
-      issueA(0);  issueB(0);  issueC(0);
-      issueA(1);  issueB(1);
-      if (2 <= n) issueA(2);
-      for (int q = 1; q <= kPrefetchAhead; ++q) prefetch_plane(q);  // what the copies above did not cover
+#pragma unroll 1
+      for (int q = -1; q <= 2; ++q) {  // planes -1 .. 2 of ring A, -1 .. 1 of ring B, plane 0 of ring C
+        if (q <= n) issueA(q);
+        if (q <= 1) issueB(q);
+        if (q == 0) issueC(0);
+      }
     }
     cta_sync<L::THREADS>();  // consumers: S of planes -1, 0, 1 formed
     cta_sync<L::THREADS>();  // consumers: register-carried planes loaded (slot 0 may be refilled)
@@ -277,7 +288,6 @@ __device__ __forceinline__ void sweep_tma_run(const TmaMaps& maps, const SweepAr
         if (q + 3 <= n) issueA(q + 3);
         if (q + 2 <= n) issueB(q + 2);
         if (q + 1 <= n - 1) issueC(q + 1);
-        prefetch_plane(q + 1 + kPrefetchAhead);
       }
       cta_sync<L::THREADS>();
     }
@@ -295,25 +305,54 @@ __device__ __forceinline__ void sweep_tma_run(const TmaMaps& maps, const SweepAr
   const float wyp = (gy < g.h - 1) ? hy2 : 0.f;
   const float wym = (gy > 0) ? hy2 : 0.f;
   const unsigned row_g = (unsigned)gy * g.ld + gx0;
+  // x faces: loop-invariant per thread (x does not change along the march)
+  const bool face_lo = gx0 == 0;
+  const bool face_hi3 = gx0 + 3 == g.w - 1;
+  const int tail = (g.w - 1 >= gx0 && g.w - 1 < gx0 + 3) ? (g.w - gx0) : 0;  // see mirror_tail
+  float wxp4[4], wxm4[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int x = gx0 + i;
+    wxp4[i] = (x < g.w - 1) ? hx2 : 0.f;
+    wxm4[i] = (x > 0) ? hx2 : 0.f;
+  }
+  // own column of a haloed plane buffer, with the in-vector face mirrored
+  auto load_own = [&](const float* plane) {
+    float4 v = ld4(plane + rc);
+    if (tail) mirror_tail(v, tail, plane[rc - 1]);
+    return v;
+  };
 
-  waitA(-1); prepass(-1);
-  waitA(0);  prepass(0);
-  waitA(1);  prepass(1);
+#pragma unroll 1
+  for (int q = -1; q <= 1; ++q) { waitA(q); prepass(q); }
   fence_proxy_async();
   cta_sync<L::THREADS>();
   waitB(-1);
   waitB(0);
   // own column, planes q-1 and q, carried in registers
-  float4 Pu = ld4(fS + (0 * 3 + 0) * HPf + rc), Pv = ld4(fS + (0 * 3 + 1) * HPf + rc),
-         Pw = ld4(fS + (0 * 3 + 2) * HPf + rc), Pp = ld4(fP + 0 * HPf + rc);
-  float4 Cu = ld4(fS + (1 * 3 + 0) * HPf + rc), Cv = ld4(fS + (1 * 3 + 1) * HPf + rc),
-         Cw = ld4(fS + (1 * 3 + 2) * HPf + rc), Cp = ld4(fP + 1 * HPf + rc);
+  float4 Pu = load_own(fS + (0 * 3 + 0) * HPf), Pv = load_own(fS + (0 * 3 + 1) * HPf),
+         Pw = load_own(fS + (0 * 3 + 2) * HPf), Pp = load_own(fP + 0 * HPf);
+  float4 Cu = load_own(fS + (1 * 3 + 0) * HPf), Cv = load_own(fS + (1 * 3 + 1) * HPf),
+         Cw = load_own(fS + (1 * 3 + 2) * HPf), Cp = load_own(fP + 1 * HPf);
   cta_sync<L::THREADS>();  // slot 0 (plane -1) is refilled by the first step's TMA: everyone must have read it
 
   int sb_c = 1, sb_n = 2;  // ring B slots of planes q and q+1
   int sd_c = 1;            // ring D slot of plane q
 #pragma unroll 1
   for (int q = 0; q < n; ++q) {
+    // Rings B and C are refilled only one step before their first use (shared memory goes to the deep
+    // ring A), so their copies must be L2 hits: every thread prefetches its own 16 B of phi and of the
+    // centre-only fields a few planes ahead (plain prefetch.global.L2; a TMA tensor prefetch of the same
+    // boxes measured slower and raised DRAM traffic by 28 %).
+    if (active) {
+      const int zp = zb + q + kPf;
+      if (zp < a.ze) {
+        const unsigned o = (unsigned)zp * (unsigned)g.ps + row_g;
+        prefetch_l2(a.fx + o); prefetch_l2(a.fy + o); prefetch_l2(a.fz + o); prefetch_l2(a.ft + o);
+        if constexpr (!KSI) prefetch_l2(a.ksi + o);
+        if (zp + 1 < g.d) prefetch_l2(a.phi + o + (unsigned)g.ps);
+      }
+    }
     waitB(q + 1);
     waitC(q);
     const int sa_c = (q + 1) & 3, sa_n = (q + 2) & 3, sc = q & 1;
@@ -326,14 +365,14 @@ __device__ __forceinline__ void sweep_tma_run(const TmaMaps& maps, const SweepAr
     const float* Dc = fD + (sd_c * L::ND) * CPf;
 
     // plane q+1 of the own column (becomes the centre of the next step)
-    const float4 Nu = ld4(Sn + 0 * HPf + rc), Nv = ld4(Sn + 1 * HPf + rc), Nw = ld4(Sn + 2 * HPf + rc),
-                 Np = ld4(Pn + rc);
+    const float4 Nu = load_own(Sn + 0 * HPf), Nv = load_own(Sn + 1 * HPf), Nw = load_own(Sn + 2 * HPf),
+                 Np = load_own(Pn);
     // x neighbours (shuffles: every lane takes part)
     float Su_xm[4], Su_xp[4], Sv_xm[4], Sv_xp[4], Sw_xm[4], Sw_xp[4], ph_xm[4], ph_xp[4];
-    x_nb<EDGE, L::LX>(Cu, Sc + 0 * HPf + rc, lx, gx0, g.w, Su_xm, Su_xp);
-    x_nb<EDGE, L::LX>(Cv, Sc + 1 * HPf + rc, lx, gx0, g.w, Sv_xm, Sv_xp);
-    x_nb<EDGE, L::LX>(Cw, Sc + 2 * HPf + rc, lx, gx0, g.w, Sw_xm, Sw_xp);
-    x_nb<EDGE, L::LX>(Cp, Pc + rc, lx, gx0, g.w, ph_xm, ph_xp);
+    x_nb<L::LX>(Cu, Sc + 0 * HPf + rc, lx, face_lo, face_hi3, Su_xm, Su_xp);
+    x_nb<L::LX>(Cv, Sc + 1 * HPf + rc, lx, face_lo, face_hi3, Sv_xm, Sv_xp);
+    x_nb<L::LX>(Cw, Sc + 2 * HPf + rc, lx, face_lo, face_hi3, Sw_xm, Sw_xp);
+    x_nb<L::LX>(Cp, Pc + rc, lx, face_lo, face_hi3, ph_xm, ph_xp);
 
     if (active) {
       const float4 Su_ym = ld4(Sc + 0 * HPf + rm), Su_yp = ld4(Sc + 0 * HPf + rp);
@@ -356,12 +395,7 @@ __device__ __forceinline__ void sweep_tma_run(const TmaMaps& maps, const SweepAr
       float numU[4], denU[4], denV[4], denW[4], rks[4], sV[4], sW[4], j12[4], j13[4], j23[4], j24[4], j34[4], dwv[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float wxp = hx2, wxm = hx2;
-        if constexpr (EDGE) {
-          const int x = gx0 + i;
-          wxp = (x < g.w - 1) ? hx2 : 0.f;
-          wxm = (x > 0) ? hx2 : 0.f;
-        }
+        const float wxp = wxp4[i], wxm = wxm4[i];
         const float gx = comp(fx4, i), gyv = comp(fy4, i), gz = comp(fz4, i), gt = comp(ft4, i);
         const float J11 = __fmul_rn(gx, gx);
         const float J22 = __fmul_rn(gyv, gyv);
@@ -444,11 +478,9 @@ __device__ __forceinline__ void sweep_tma_run(const TmaMaps& maps, const SweepAr
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         if (!ok[i]) {  // an operand outside the fast path's range (zero, tiny, huge, NaN): IEEE division
-          rdu[i] = __fdiv_rn(numU[i], denU[i]);
-          const float ndv = __fmaf_rn(-j23[i], dwv[i], __fmaf_rn(-j12[i], rdu[i], -j24[i]));
-          rdv[i] = __fdiv_rn(__fmaf_rn(rks[i], ndv, sV[i]), denV[i]);
-          const float ndw = __fmaf_rn(-j23[i], rdv[i], __fmaf_rn(-j13[i], rdu[i], -j34[i]));
-          rdw[i] = __fdiv_rn(__fmaf_rn(rks[i], ndw, sW[i]), denW[i]);
+          const float3 r = slow_voxel(numU[i], denU[i], denV[i], denW[i], rks[i], sV[i], sW[i], j12[i], j13[i], j23[i],
+                                      j24[i], j34[i], dwv[i]);
+          rdu[i] = r.x; rdv[i] = r.y; rdw[i] = r.z;
         }
       }
       const unsigned o = (unsigned)(zb + q) * (unsigned)g.ps + row_g;
@@ -477,10 +509,7 @@ __global__ void __launch_bounds__(TL<BX, BY, KSI>::THREADS, 2)
     sweep_tma_kernel(const __grid_constant__ TmaMaps maps, const SweepArgs a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-  const int tx0 = blockIdx.x * BX;
-  const bool edge = (tx0 == 0) || (tx0 + BX > a.g.w - 1);  // CTA-uniform: the tile touches an x face
-  if (edge) sweep_tma_run<BX, BY, KSI, true>(maps, a, smem);
-  else sweep_tma_run<BX, BY, KSI, false>(maps, a, smem);
+  sweep_tma_run<BX, BY, KSI>(maps, a, smem);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -598,7 +627,7 @@ static int launch_shape(const SweepArgs& a0, int zchunk_len, cudaStream_t st) {
 }
 
 bool sweep_tma_usable(const Dims& g, int variant) {
-  if (variant != SWEEP_VARIANT_TMA_64x8 && variant != SWEEP_VARIANT_TMA_32x16) return false;
+  if (!sweep_variant_is_tma(variant)) return false;
   if (g.w < 8 || g.h < 2 || (g.ld & 3)) return false;
   const int by = variant == SWEEP_VARIANT_TMA_64x8 ? 8 : 16;
   return (g.h + by - 1) / by <= 65535 && encode_fn() != nullptr;

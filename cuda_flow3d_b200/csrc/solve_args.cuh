@@ -28,10 +28,11 @@ struct SweepArgs {
 struct TuneCfg {
   int vec;      // register kernel: voxels per lane (1, 2, 4)
   int nchunks;  // z chunks (0 = static heuristic)
-  int variant;  // 0 = register-marching warp kernel; 1.. = TMA tile shapes (kernels_sweep_tma.cu)
+  int variant;  // SWEEP_VARIANT_*
 };
 
 enum { SWEEP_VARIANT_REG = 0, SWEEP_VARIANT_TMA_64x8 = 1, SWEEP_VARIANT_TMA_32x16 = 2, SWEEP_VARIANT_COUNT };
+inline bool sweep_variant_is_tma(int v) { return v == SWEEP_VARIANT_TMA_64x8 || v == SWEEP_VARIANT_TMA_32x16; }
 
 // TMA-staged sweep (kernels_sweep_tma.cu); returns FLOW3D_ERR_UNSUPPORTED when the level cannot use it
 int launch_sweep_tma(const SweepArgs& a, int variant, int zchunk_len, cudaStream_t st);
