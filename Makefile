@@ -16,7 +16,7 @@ CU_OBJS   := $(CU_SRCS:.cu=.o)
 HOST_SRCS := $(wildcard $(PKG)/host/*.cpp)
 HOST_OBJS := $(HOST_SRCS:.cpp=.o)
 
-all: $(LIB) oracle apps
+all: $(LIB) $(MGPU_LIB) oracle apps
 
 $(CSRC)/kernels_median.o: $(CSRC)/median_net_27.inc $(CSRC)/median_net_125.inc $(CSRC)/median5_sort25.inc
 
@@ -34,6 +34,13 @@ $(PKG)/host/%.o: $(PKG)/host/%.cpp
 
 $(LIB): $(CU_OBJS) $(HOST_OBJS)
 	$(NVCC) $(ARCH) -ccbin $(HOSTCXX) -shared -o $@ $^
+
+# multi-GPU: the z-sharded solver (host C++ over the C ABI above + NCCL); a separate library so that the
+# single-GPU library carries no NCCL dependency
+MGPU_LIB  := $(PKG)/libflow3d_b200_mgpu.so
+$(MGPU_LIB): $(CSRC)/sharded_solver.cu include/flow3d_mgpu_c.h include/flow3d_c.h $(LIB)
+	$(NVCC) $(ARCH) -ccbin $(HOSTCXX) -std=c++17 -O2 -lineinfo -Xcompiler -fPIC,-O2,-fno-fast-math,-ffp-contract=off \
+	  -Iinclude -shared -o $@ $< -L$(PKG) -lflow3d_b200 -lnccl -Xlinker -rpath -Xlinker '$$ORIGIN'
 
 oracle:
 	$(MAKE) -C oracle liboracle.so
@@ -53,7 +60,7 @@ ref:
 	bash oracle/build_ref.sh
 
 clean:
-	rm -f $(CU_OBJS) $(HOST_OBJS) $(CSRC)/*.ptxas.log $(LIB) $(APPS)
+	rm -f $(CU_OBJS) $(HOST_OBJS) $(CSRC)/*.ptxas.log $(LIB) $(MGPU_LIB) $(APPS)
 	$(MAKE) -C oracle clean
 
 .PHONY: all oracle ref clean apps

@@ -123,6 +123,9 @@ def parse():
     ap.add_argument("--levels", type=int, default=0,
                     help="profiling aid: run only the finest LEVELS pyramid levels (NOT the benchmark workload; the "
                          "JSON line says so)")
+    ap.add_argument("--warp-levels", type=int, default=0, help="N>1: override warp_levels_count (config 5 uses 60-80)")
+    ap.add_argument("--no-parity-check", action="store_true", help="N>1: skip the 256^3 sharded-vs-single check")
+    ap.add_argument("--no-strong-ref", action="store_true", help="N>1: skip the same-size single-GPU solve")
     ap.add_argument("--replicas", action="store_true", help="N>1: independent 512^3 replicas instead of one sharded solve")
     return ap.parse_args()
 
@@ -311,139 +314,282 @@ def run_reference(args, rank, world):
 
 # ---------------------------------------------------------------------------------------------------
 def run_sharded(args, rank, world, local_rank):
-    """N > 1: ONE volume pair (BASELINE configs[3]: synthetic 1024^3) z-sharded over the N GPUs,
-    neighbour halo exchange over NVLink (NCCL send/recv), cuda_flow3d_b200/dist.py."""
+    """N > 1: ONE volume pair (BASELINE configs[3]: synthetic 1024^3; --size 2048 = configs[4]) z-sharded over
+    the N GPUs by the C++ sharded solver (libflow3d_b200_mgpu.so: C-ABI slab stages + one grouped NCCL
+    send/recv of the ghost planes per outer iteration, on the solve's stream).  torch.distributed is only
+    the launcher-side plumbing here: it hands out the NCCL id and reduces the timings."""
+    import hashlib
     import torch
     import torch.distributed as dist
     import cuda_flow3d_b200 as pkg
-    from cuda_flow3d_b200.dist import CabiBackend, ShardedFlowSolver
+    import cuda_flow3d_b200.mgpu as mgpu
     L = pkg.load()
     pkg.require_device()
     torch.cuda.set_device(local_rank)
+    pkg._lib.check(L.flow3d_set_device(local_rank), "set_device")
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    be = CabiBackend(local_rank)
+    dev = torch.device("cuda", local_rank)
     n = args.size or 1024
     W = H = D = n
     P = dict(pkg.DEFAULTS)
-    ld = be.ld(W)
-    dev = be.dev
+    if args.warp_levels > 0:
+        P["warp_levels_count"] = args.warp_levels
+    params = pkg.api.make_params(P)
+    ld = int(L.flow3d_aligned_ld(W))
     st = torch.cuda.current_stream()
     sp = C.c_void_p(st.cuda_stream)
-    # every rank holds only the z-slab of the raw frames it needs (own planes + frame ghost + blur halo),
-    # generated on the device
-    from cuda_flow3d_b200.dist import ShardedFrames
     ghost = 32
-    z_lo, z_hi = ShardedFrames.input_planes(D, rank, world, P["gaussian_sigma"], ghost)
-    nzl = z_hi - z_lo
-    f0 = torch.empty((nzl, H, ld), dtype=torch.float32, device=dev)
-    f1 = torch.empty((nzl, H, ld), dtype=torch.float32, device=dev)
-    pkg._lib.check(L.flow3d_synth_pair(W, H, D, z_lo, nzl, ld, SEED, C.c_void_p(f0.data_ptr()),
-                                       C.c_void_p(f1.data_ptr()), None, None, None, sp), "synth")
-    solver = ShardedFlowSolver(be)
 
     def barrier():
         dist.barrier()
         torch.cuda.synchronize()
 
+    def make_solver(w, h, d):
+        uid = [mgpu.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        return mgpu.ShardedSolver(w, h, d, local_rank, rank, world, uid[0])
+
+    def synth_slab(w, h, d, lo, hi):
+        l = int(L.flow3d_aligned_ld(w))
+        a0 = torch.empty(((hi - lo), h, l), dtype=torch.float32, device=dev)
+        a1 = torch.empty(((hi - lo), h, l), dtype=torch.float32, device=dev)
+        pkg._lib.check(L.flow3d_synth_pair(w, h, d, lo, hi - lo, l, SEED, C.c_void_p(a0.data_ptr()),
+                                           C.c_void_p(a1.data_ptr()), None, None, None, sp), "synth")
+        return a0, a1, l
+
+    # ---- on-hardware parity of THIS build's sharded path: 256^3 sharded vs the same pair on rank 0 alone ------
+    parity = None
+    if not args.no_parity_check:
+        m = 256
+        ps = make_solver(m, m, m)
+        ps.set_thresholds(8, 1)
+        lo, hi = mgpu.input_planes(m, rank, world, P["gaussian_sigma"], ghost)
+        q0, q1, ql = synth_slab(m, m, m, lo, hi)
+        pa, pb = ps.output_planes(params)
+        qo = [torch.empty(((pb - pa), m, ql), dtype=torch.float32, device=dev) for _ in range(3)]
+        a, b = ps.compute(q0.data_ptr(), q1.data_ptr(), lo, hi - lo, ql, params, ghost, [t.data_ptr() for t in qo],
+                          pb - pa, st.cuda_stream)
+        torch.cuda.synchronize()
+        mine = [(a, b, hashlib.sha256(t[:, :, :m].contiguous().cpu().numpy().tobytes()).hexdigest()) for t in qo]
+        pst = ps.stats()
+        ps.destroy()
+        allr = [None] * world
+        dist.all_gather_object(allr, mine)
+        if rank == 0:
+            g0, g1, gl = synth_slab(m, m, m, 0, m)
+            so = [torch.empty((m, m, gl), dtype=torch.float32, device=dev) for _ in range(3)]
+            single = C.c_void_p()
+            pkg._lib.check(L.flow3d_solver_create(m, m, m, local_rank, C.byref(single)), "solver_create")
+            pkg._lib.check(L.flow3d_solver_compute_device(single, C.c_void_p(g0.data_ptr()), C.c_void_p(g1.data_ptr()), gl,
+                                                          C.byref(params), C.c_void_p(so[0].data_ptr()),
+                                                          C.c_void_p(so[1].data_ptr()), C.c_void_p(so[2].data_ptr()), sp),
+                           "compute_device")
+            torch.cuda.synchronize()
+            L.flow3d_solver_destroy(single)
+            bad = 0
+            for r in range(world):
+                for c in range(3):
+                    ra, rb, sha = allr[r][c]
+                    ref = hashlib.sha256(so[c][ra:rb, :, :m].contiguous().cpu().numpy().tobytes()).hexdigest()
+                    bad += int(ref != sha)
+            parity = {"workload": "synthetic 256^3 pair, default parameters, sharded over %d GPUs vs the single-GPU "
+                                  "solver on rank 0 (sha256 of every rank's planes of u, v, w)" % world,
+                      "bitwise_equal": bad == 0, "mismatching_rank_components": bad,
+                      "sharded_levels": pst["sharded_levels"], "replicated_levels": pst["replicated_levels"]}
+            del g0, g1, so
+        del q0, q1, qo
+        torch.cuda.empty_cache()
+
+    # ---- the benchmark solve --------------------------------------------------------------------------------
+    z_lo, z_hi = mgpu.input_planes(D, rank, world, P["gaussian_sigma"], ghost)
+    nzl = z_hi - z_lo
+    f0, f1, _ = synth_slab(W, H, D, z_lo, z_hi)
+    solver = make_solver(W, H, D)
+    pa, pb = solver.output_planes(params)
+    outs = [torch.empty(((pb - pa), H, ld), dtype=torch.float32, device=dev) for _ in range(3)]
+    t_tune = time.perf_counter()
+    solver.tune(params)
+    t_tune = time.perf_counter() - t_tune
+
     def step():
-        return solver.compute_slabs(f0, f1, z_lo, (W, H, D), P, return_device=True, frame_ghost=ghost)
+        return solver.compute(f0.data_ptr(), f1.data_ptr(), z_lo, nzl, ld, params, ghost, [t.data_ptr() for t in outs],
+                              pb - pa, st.cuda_stream)
 
     for _ in range(args.warmup):
         step()
     barrier()
-    solver.profile = True
-    solver.sweep_events = []
-    solver.phase_marks = []
-    for k in solver.stats:
-        solver.stats[k] = 0
+    solver.set_profiling(True)
     L.flow3d_reset_launch_count()
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    phases = {}
+    stats = {}
     e0.record(st)
     for _ in range(args.steps):
-        a, b, flow = step()
+        a, b = step()
+        for k, v in solver.phase_ms().items():
+            phases[k] = phases.get(k, 0.0) + v
+        for k, v in solver.stats().items():
+            stats[k] = max(stats.get(k, 0.0), v) if k == "peak_device_bytes" else stats.get(k, 0.0) + v
     e1.record(st)
     barrier()
     clocks = sampler.stop()
+    solver.set_profiling(False)
     launches = int(L.flow3d_launch_count())
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
     value = (W * H * D) / (ms_per_step / 1000.0) / 1e6
-    sw_ms, sw_units, phi_units = solver.sweep_profile()
-    phases = {k: v / args.steps for k, v in solver.phase_profile().items()}
-    solver.profile = False
-    stats = dict(solver.stats)
+    phases = {k: v / args.steps for k, v in phases.items()}
+    halo = torch.tensor([phases.get("halo_exchange", 0.0), phases.get("solver", 0.0)], device=dev)
+    halo_max = halo.clone()
+    dist.all_reduce(halo_max, op=dist.ReduceOp.MAX)
+    mem = torch.tensor([stats.get("peak_device_bytes", 0.0) + 2.0 * nzl * H * ld * 4 + 3.0 * (pb - pa) * H * ld * 4],
+                       device=dev)
+    dist.all_reduce(mem, op=dist.ReduceOp.MAX)
 
-    # e2e: every rank uploads both (replicated) frames from pinned host memory and downloads its shard
+    # ---- accuracy: endpoint error against the analytic motion, reduced over the ranks ------------------------
+    tr = [torch.empty(((b - a), H, ld), dtype=torch.float32, device=dev) for _ in range(3)]
+    pkg._lib.check(L.flow3d_synth_pair(W, H, D, a, b - a, ld, SEED, None, None, C.c_void_p(tr[0].data_ptr()),
+                                       C.c_void_p(tr[1].data_ptr()), C.c_void_p(tr[2].data_ptr()), sp), "synth truth")
+    sq = None
+    for o, tt in zip(outs, tr):
+        dlt = (o[:, :, :W] - tt[:, :, :W]).double()
+        sq = dlt * dlt if sq is None else sq + dlt * dlt
+    e = sq.sqrt()
+    mg = 16
+    z0i, z1i = max(a, mg), min(b, D - mg)
+    inner = e[z0i - a:z1i - a, mg:-mg, mg:-mg] if z1i > z0i else e[0:0]
+    acc = torch.tensor([float(e.sum().item()), float(e.numel()), float(inner.sum().item()), float(inner.numel())],
+                       dtype=torch.float64, device=dev)
+    dist.all_reduce(acc)
+    epe = {"mean": float(acc[0] / acc[1]), "interior_mean": float(acc[2] / max(acc[3], 1.0)), "unit": "voxel",
+           "note": "flow vs the analytic rigid motion, all ranks' planes; interior = 16-voxel margin removed"}
+    del tr, sq, e
+
+    # ---- e2e: every rank uploads its slab of both raw frames from pinned host memory, downloads its planes ---
     e2e = None
     if not args.no_e2e:
         ok = torch.ones(1, device=dev)
         try:
             h0 = torch.empty((nzl, H, ld), dtype=torch.float32, pin_memory=True)
             h1 = torch.empty((nzl, H, ld), dtype=torch.float32, pin_memory=True)
-            ho = [torch.empty((b - a, H, ld), dtype=torch.float32, pin_memory=True) for _ in range(3)]
+            ho = [torch.empty((pb - pa, H, ld), dtype=torch.float32, pin_memory=True) for _ in range(3)]
         except Exception:  # not enough lockable host memory on this box
             ok.zero_()
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        bi, bo = 2 * nzl * H * ld * 4, 3 * (pb - pa) * H * ld * 4
         if float(ok.item()) > 0:
             h0.copy_(f0)
             h1.copy_(f1)
-            step()  # untimed: lets the allocator settle after the pinned allocations
             barrier()
             x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             x0.record(st)
             f0.copy_(h0, non_blocking=True)
             f1.copy_(h1, non_blocking=True)
-            a, b, flow = step()
+            step()
             for c in range(3):
-                ho[c].copy_(flow[c], non_blocking=True)
+                ho[c].copy_(outs[c], non_blocking=True)
             x1.record(st)
             barrier()
             t = torch.tensor([x0.elapsed_time(x1)], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e_ms = float(t.item())
-            e2e = {"value": (W * H * D) / (e_ms / 1000.0) / 1e6, "unit": "Mvoxel/s",
-                   "h2d_bytes_per_step": 2 * nzl * H * ld * 4, "d2h_bytes_per_step": 3 * (b - a) * H * ld * 4,
-                   "ms_per_step": e_ms, "steps": 1, "host_memory": "pinned",
+            e2e = {"value": (W * H * D) / (e_ms / 1000.0) / 1e6, "unit": "Mvoxel/s", "h2d_bytes_per_step": bi,
+                   "d2h_bytes_per_step": bo, "ms_per_step": e_ms, "steps": 1, "host_memory": "pinned",
                    "note": "per rank: its z-slab of both raw frames up (own planes + %d ghost + blur halo), own "
                            "z-shard of the flow down" % ghost}
+            del h0, h1, ho
         else:
-            e2e = {"value": None, "unit": "Mvoxel/s", "h2d_bytes_per_step": 2 * nzl * H * ld * 4,
-                   "d2h_bytes_per_step": 3 * (b - a) * H * ld * 4,
+            e2e = {"value": None, "unit": "Mvoxel/s", "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo,
                    "note": "pinned host allocation failed on this box; end-to-end run skipped"}
+
+    # ---- strong scaling: the SAME volume on rank 0 alone, same job (skipped when it cannot fit one GPU) -------
+    strong = None
+    if not args.no_strong_ref:
+        need = float(L.flow3d_solver_workspace_bytes(W, H, D)) + 5.0 * ld * H * D * 4
+        free_b, _tot = torch.cuda.mem_get_info()
+        del outs
+        torch.cuda.empty_cache()
+        if rank == 0:
+            free_b, _tot = torch.cuda.mem_get_info()
+            if need < 0.92 * free_b:
+                g0, g1, _ = synth_slab(W, H, D, 0, D)
+                so = [torch.empty((D, H, ld), dtype=torch.float32, device=dev) for _ in range(3)]
+                single = C.c_void_p()
+                pkg._lib.check(L.flow3d_solver_create(W, H, D, local_rank, C.byref(single)), "solver_create")
+                pkg._lib.check(L.flow3d_solver_tune(single, C.byref(params)), "solver_tune")
+
+                def one():
+                    pkg._lib.check(L.flow3d_solver_compute_device(
+                        single, C.c_void_p(g0.data_ptr()), C.c_void_p(g1.data_ptr()), ld, C.byref(params),
+                        C.c_void_p(so[0].data_ptr()), C.c_void_p(so[1].data_ptr()), C.c_void_p(so[2].data_ptr()), sp), "solve")
+                one()
+                torch.cuda.synchronize()
+                y0, y1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                y0.record(st)
+                one()
+                y1.record(st)
+                torch.cuda.synchronize()
+                t1 = y0.elapsed_time(y1)
+                L.flow3d_solver_destroy(single)
+                strong = {"size": "%d^3" % n, "t_1gpu_ms": t1, "t_%dgpu_ms" % world: ms_per_step,
+                          "speedup": t1 / ms_per_step, "efficiency": t1 / ms_per_step / world,
+                          "note": "same volume, same parameters, single-GPU solver on rank 0 of this job (1 warm-up + 1 "
+                                  "timed solve, CUDA events)"}
+            else:
+                strong = {"size": "%d^3" % n, "skipped": "the single-GPU solver needs %.0f GB for this volume" % (need / 1e9)}
+        barrier()
+
     if rank == 0:
         peak, peak_src = hbm_peak()
-        achieved = (SWEEP_BYTES * sw_units + PHIKSI_BYTES * phi_units) / (sw_ms / 1000.0) / 1e9 if sw_ms > 0 else 0.0
+        sw_ms = phases.get("solver", 0.0) * args.steps
+        sw_units, phi_units = stats.get("voxel_sweeps", 0.0), stats.get("phi_voxels", 0.0)
+        achieved = (SWEEP_BYTES * sw_units + 28.0 * phi_units) / (sw_ms / 1000.0) / 1e9 if sw_ms > 0 else 0.0
         nsum, nlev = level_voxel_sum(pkg, W, H, D, P)
         line = {
             "metric": "Mvoxel/s per full pyramid flow solve", "value": value, "unit": "Mvoxel/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "synthetic %d^3 pair (BASELINE configs[3]) z-sharded over %d GPUs, default "
-                                   "parameters (%d levels x 40 outer x 5 inner sweeps, median 5, sigma 2)" % (n, world, nlev),
-                       "parallelism": "z-slabs, %d ghost planes, one NCCL send/recv neighbour exchange per outer "
-                                      "iteration; frames sharded too (coarse level frames assembled by all-gather); "
-                                      "levels too thin to shard are replicated" % (P["inner_iterations_count"] + 1),
+            "config": {"workload": "synthetic %d^3 pair with known rigid motion (BASELINE configs[%d]) z-sharded over %d "
+                                   "GPUs, default parameters: warp_levels_count %d, scale 0.95, 40 outer x 5 inner sweeps, "
+                                   "median 5, sigma 2" % (n, 4 if n >= 2048 else 3, world, P["warp_levels_count"]),
+                       "parallelism": "z-slabs, %d ghost planes, C++ sharded solver (libflow3d_b200_mgpu.so): one grouped "
+                                      "ncclSend/ncclRecv of the ghost planes per outer iteration on the solve's stream; "
+                                      "frames sharded too (coarse level frames assembled by all-gather); levels too thin "
+                                      "to shard are computed by every rank (replicated, not gathered to one GPU: same "
+                                      "wall time, no scatter)" % (P["inner_iterations_count"] + 1),
+                       "pyramid_levels": nlev, "level_voxels": nsum, "inputs_larger_than_l2": True,
+                       "sharded_levels_per_step": stats.get("sharded_levels", 0) / max(1, args.steps),
+                       "replicated_levels_per_step": stats.get("replicated_levels", 0) / max(1, args.steps),
                        "frame_gathers_per_step": stats.get("frame_gathers", 0) / max(1, args.steps),
-                       "inputs_larger_than_l2": True, "level_voxels": nsum,
-                       "sharded_levels_per_step": stats["sharded_levels"] / max(1, args.steps),
-                       "replicated_levels_per_step": stats["replicated_levels"] / max(1, args.steps),
-                       "halo_bytes_sent_per_step_rank0": stats["exchange_bytes"] / max(1, args.steps),
-                       "parity": "bit-identical to the single-GPU solve (tests/test_dist_gpu.py)"},
-            "clocks": clocks, "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "solver outer iterations on rank 0 (1 phi_ksi_kernel + 5 sweep_kernel "
-                                                    "launches each, on its z-slab incl. ghost planes)",
+                       "halo_exchanges_per_step": stats.get("exchanges", 0) / max(1, args.steps),
+                       "halo_bytes_sent_per_step_rank0": stats.get("exchange_bytes_sent", 0) / max(1, args.steps),
+                       "device_bytes_high_water_max_over_ranks": float(mem.item())},
+            "clocks": clocks, "gpu_launches": launches, "tune_seconds_untimed": t_tune,
+            "roofline": {"bound": "hbm", "kernel": "solver outer iterations on rank 0 (1 phi + 5 sweep launches each, on "
+                                                    "its z-slab incl. ghost planes)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_voxel_sweep": SWEEP_BYTES,
-                         "algorithmic_bytes_per_phi_ksi_voxel": PHIKSI_BYTES,
-                         "voxel_sweeps": sw_units, "phi_ksi_voxels": phi_units, "traffic": None},
+                         "algorithmic_bytes_per_phi_voxel": 28.0, "voxel_sweeps": sw_units, "phi_voxels": phi_units,
+                         "traffic": None},
+            "phase_ms_per_step_rank0": phases,
+            "halo_exchange_fraction_of_step": {"rank0": phases.get("halo_exchange", 0.0) / ms_per_step,
+                                               "max_over_ranks": float(halo_max[0].item()) / ms_per_step,
+                                               "note": "device time between the end of an outer iteration's kernels and "
+                                                       "the end of its NCCL group on the same stream: transfer + waiting "
+                                                       "for the slower neighbour"},
+            "endpoint_error": epe,
         }
-        line["phase_ms_per_step_rank0"] = phases
+        if parity:
+            line["parity_check"] = parity
+        if strong:
+            line["strong_scaling"] = strong
         if e2e:
             line["e2e"] = e2e
         emit(line)
+    solver.destroy()
     dist.destroy_process_group()
 
 

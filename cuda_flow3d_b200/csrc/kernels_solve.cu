@@ -615,12 +615,12 @@ static bool tune_lookup(const TuneKey& k, TuneCfg* c) {
   *c = it->second;
   return true;
 }
-// whole-level launches are keyed by their exact depth; slab launches (ranges that shrink sweep by
-// sweep) share a key per 16 planes
+// whole-level launches are keyed by their depth; slab launches (ranges that shrink sweep by sweep inside
+// one local buffer) by the depth of that buffer
 static TuneKey tune_key(int kernel, const Dims& g, ZRange zr) {
   const int nz = zr.end - zr.begin;
   const bool whole = zr.begin == 0 && zr.end == g.d && g.d == g.dg;
-  return TuneKey{current_device(), kernel, g.w, g.h, g.ld, whole ? -nz : (nz + 15) / 16};
+  return TuneKey{current_device(), kernel, g.w, g.h, g.ld, whole ? -nz : g.d};
 }
 static inline int chunk_len(int nz, int nchunks) {
   if (nchunks < 1) nchunks = 1;
