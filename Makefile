@@ -9,6 +9,7 @@ NVFLAGS   := $(ARCH) -ccbin $(HOSTCXX) -std=c++17 -O3 -lineinfo -fmad=false -Xco
 PKG       := cuda_flow3d_b200
 CSRC      := $(PKG)/csrc
 LIB       := $(PKG)/libflow3d_b200.so
+MGPU_LIB  := $(PKG)/libflow3d_b200_mgpu.so
 CU_SRCS   := $(CSRC)/flow3d_cabi.cu $(CSRC)/kernels_solve.cu $(CSRC)/kernels_sweep_tma.cu $(CSRC)/kernels_pyramid.cu \
              $(CSRC)/kernels_warp.cu $(CSRC)/kernels_median.cu $(CSRC)/kernels_synth.cu \
              $(CSRC)/kernels_diag.cu
@@ -37,7 +38,6 @@ $(LIB): $(CU_OBJS) $(HOST_OBJS)
 
 # multi-GPU: the z-sharded solver (host C++ over the C ABI above + NCCL); a separate library so that the
 # single-GPU library carries no NCCL dependency
-MGPU_LIB  := $(PKG)/libflow3d_b200_mgpu.so
 $(MGPU_LIB): $(CSRC)/sharded_solver.cu include/flow3d_mgpu_c.h include/flow3d_c.h $(LIB)
 	$(NVCC) $(ARCH) -ccbin $(HOSTCXX) -std=c++17 -O2 -lineinfo -Xcompiler -fPIC,-O2,-fno-fast-math,-ffp-contract=off \
 	  -Iinclude -shared -o $@ $< -L$(PKG) -lflow3d_b200 -lnccl -Xlinker -rpath -Xlinker '$$ORIGIN'

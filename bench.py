@@ -141,6 +141,17 @@ class ClockSampler:
         self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
         self.proc = None
         self.idx = gpu_index
+        self.offset = 0
+
+    def mark(self):
+        """the timed region starts here: only samples written after this point are used.  (The sampler is
+        STARTED before the warm-up steps: nvidia-smi's NVML start-up takes the driver's global lock for
+        0.5-2 s, which showed up as a stall at the head of the timed region when it was started there.)"""
+        try:
+            self.f.flush()
+            self.offset = os.path.getsize(self.path)
+        except Exception:
+            self.offset = 0
 
     def start(self):
         try:
@@ -164,7 +175,9 @@ class ClockSampler:
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         try:
-            for line in open(self.path):
+            fh = open(self.path)
+            fh.seek(self.offset)
+            for line in fh:
                 p = [x.strip() for x in line.split(",")]
                 if len(p) < 9:
                     continue
@@ -415,13 +428,14 @@ def run_sharded(args, rank, world, local_rank):
         return solver.compute(f0.data_ptr(), f1.data_ptr(), z_lo, nzl, ld, params, ghost, [t.data_ptr() for t in outs],
                               pb - pa, st.cuda_stream)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
     solver.set_profiling(True)
     L.flow3d_reset_launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     phases = {}
     stats = {}
@@ -442,6 +456,8 @@ def run_sharded(args, rank, world, local_rank):
     ms_per_step = float(t.item()) / args.steps
     value = (W * H * D) / (ms_per_step / 1000.0) / 1e6
     phases = {k: v / args.steps for k, v in phases.items()}
+    all_phases = [None] * world
+    dist.all_gather_object(all_phases, {k: round(v, 1) for k, v in phases.items()})
     halo = torch.tensor([phases.get("halo_exchange", 0.0), phases.get("solver", 0.0)], device=dev)
     halo_max = halo.clone()
     dist.all_reduce(halo_max, op=dist.ReduceOp.MAX)
@@ -574,7 +590,7 @@ def run_sharded(args, rank, world, local_rank):
                          "peak_source": peak_src, "algorithmic_bytes_per_voxel_sweep": SWEEP_BYTES,
                          "algorithmic_bytes_per_phi_voxel": 28.0, "voxel_sweeps": sw_units, "phi_voxels": phi_units,
                          "traffic": None},
-            "phase_ms_per_step_rank0": phases,
+            "phase_ms_per_step_rank0": phases, "phase_ms_per_step_all_ranks": all_phases,
             "halo_exchange_fraction_of_step": {"rank0": phases.get("halo_exchange", 0.0) / ms_per_step,
                                                "max_over_ranks": float(halo_max[0].item()) / ms_per_step,
                                                "note": "device time between the end of an outer iteration's kernels and "
@@ -684,12 +700,13 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step_device()
     barrier()
     L.flow3d_reset_launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage_ms = np.zeros(8)
     stage_units = np.zeros(8)

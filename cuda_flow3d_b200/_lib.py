@@ -97,6 +97,9 @@ SIGNATURES = {
                                                C.POINTER(ZSlab), _f3] + [_vp] * 5),
     "flow3d_outer_iteration_slab": (C.c_int, [_vp] * 15 + [_sz3, C.c_size_t, C.POINTER(ZSlab), _f3, C.c_size_t,
                                                 C.c_float, C.c_float, C.c_float, C.POINTER(C.c_int), _vp]),
+    "flow3d_outer_iteration_slab_part": (C.c_int, [_vp] * 15 + [_sz3, C.c_size_t, C.POINTER(ZSlab), _f3, C.c_size_t,
+                                                     C.c_float, C.c_float, C.c_float, C.c_int, C.c_size_t, C.c_size_t,
+                                                     C.POINTER(C.c_int), _vp]),
     "flow3d_median_slab": (C.c_int, [_vp, _vp, _sz3, C.c_size_t, C.POINTER(ZSlab), C.c_size_t, _vp]),
     "flow3d_resample_slab": (C.c_int, [_vp, _sz3, C.c_size_t, C.POINTER(ZSlab), _vp, _sz3, C.c_size_t, C.POINTER(ZSlab),
                                        _vp, _vp, _vp]),

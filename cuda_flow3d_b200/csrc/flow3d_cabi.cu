@@ -1,6 +1,7 @@
 // flow3d_cabi.cu -- the C ABI (include/flow3d_c.h): argument checking, the stage wrappers and the
 // solver object that runs the coarse-to-fine loop of OpticalFlowE::ComputeFlow
 // (reference: src/optical_flow/optical_flow_e.cpp:132-601) on compact per-level device buffers.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -747,6 +748,60 @@ int flow3d_warp_derivatives_slab(const float* f0, const float* f1, size_t f1_z0_
                                  h[0], h[1], h[2], fx, fy, fz, ft, S(stream));
 }
 
+// The outer iteration of a z-slab, optionally split for communication overlap.  part 0: everything (phi on
+// [z_begin,z_end), sweep j on the range shrunk by j planes on every side that is not a global face).
+// part 1 ("early"): only the planes whose values do not depend on the ghost planes outside the owned range
+// [own_begin, own_end): step j (phi = 0, sweep j) on [own_begin+j+1, own_end-j-1), extended to the buffer
+// end on a side without ghost planes -- a value at plane p after step j depends on the starting iterate on
+// [p-j-1, p+j+1] only.  part 2 ("late"): the remaining planes of every step, to be run once the ghosts
+// have arrived.  Early and late launches touch disjoint planes of every buffer at every step (the late
+// part of step j reads planes <= own_begin+j+1 of the buffer the early part of step j+1 writes from
+// own_begin+j+2 on), so early(i+1) may overlap the exchange that follows late(i).
+static int outer_iteration_parts(const float* fx, const float* fy, const float* fz, const float* ft, const float* u,
+                                 const float* v, const float* w, float* du, float* dv, float* dw, float* tdu,
+                                 float* tdv, float* tdw, float* phi, float* ksi, const Dims& g, ZRange r0,
+                                 const float* h, size_t inner, float alpha, float eps_smooth, float eps_data, int part,
+                                 int own_begin, int own_end, int* result_in_tmp, cudaStream_t st) {
+  const bool lo_face = (g.z0g + r0.begin) == 0, hi_face = (g.z0g + r0.end) == g.dg;
+  // ksi is pointwise in the iterate, so the first sweep computes it (every later sweep of the iteration
+  // works inside the first one's range)
+  const bool fuse = fuse_ksi() && inner > 0;
+  float *a0 = du, *a1 = dv, *a2 = dw, *b0 = tdu, *b1 = tdv, *b2 = tdw;
+  for (size_t j = 0; j <= inner; ++j) {
+    const ZRange full{(lo_face || j == 0) ? r0.begin : r0.begin + (int)j, (hi_face || j == 0) ? r0.end : r0.end - (int)j};
+    // a side has ghosts when the buffer holds planes beyond the owned range there
+    ZRange early = full;
+    if (own_begin > 0) early.begin = std::max(full.begin, own_begin + (int)j + 1);
+    if (own_end < g.d) early.end = std::min(full.end, own_end - (int)j - 1);
+    if (early.end < early.begin) early.end = early.begin;
+    ZRange todo[2];
+    int n = 0;
+    if (part == 0) todo[n++] = full;
+    else if (part == 1) todo[n++] = early;
+    else {
+      todo[n++] = ZRange{full.begin, std::min(early.begin, full.end)};
+      todo[n++] = ZRange{std::max(early.end, full.begin), full.end};
+    }
+    for (int k = 0; k < n; ++k) {
+      if (todo[k].end <= todo[k].begin) continue;
+      if (j == 0) {
+        F3D_TRY(launch_phi_ksi(fx, fy, fz, ft, u, v, w, du, dv, dw, g, todo[k], h[0], h[1], h[2], eps_smooth, eps_data,
+                               phi, fuse ? nullptr : ksi, st));
+      } else {
+        F3D_TRY(launch_sweep(fx, fy, fz, ft, u, v, w, a0, a1, a2, phi, ksi, g, todo[k], h[0], h[1], h[2], alpha, b0, b1,
+                             b2, st, (fuse && j == 1) ? ksi : nullptr, eps_data));
+      }
+    }
+    if (j >= 1) {
+      std::swap(a0, b0);
+      std::swap(a1, b1);
+      std::swap(a2, b2);
+    }
+  }
+  *result_in_tmp = (a0 == tdu) ? 1 : 0;
+  return FLOW3D_OK;
+}
+
 int flow3d_outer_iteration_slab(const float* fx, const float* fy, const float* fz, const float* ft,
                                 const float* u, const float* v, const float* w, float* du, float* dv,
                                 float* dw, float* tdu, float* tdv, float* tdw, float* phi, float* ksi,
@@ -758,25 +813,26 @@ int flow3d_outer_iteration_slab(const float* fx, const float* fy, const float* f
   F3D_TRY(check_slab(dims, slab));
   if (!h || !slab || !result_in_tmp) return FLOW3D_ERR_INVALID_ARG;
   const Dims g = make_slab_dims(dims, ld, slab);
-  const ZRange r0 = make_range(g, slab);
-  const bool lo_face = (g.z0g + r0.begin) == 0, hi_face = (g.z0g + r0.end) == g.dg;
-  cudaStream_t st = S(stream);
-  // ksi is pointwise in the iterate, so the first sweep computes it (every later sweep of the iteration
-  // works inside the first one's range)
-  const bool fuse = fuse_ksi() && inner > 0;
-  F3D_TRY(launch_phi_ksi(fx, fy, fz, ft, u, v, w, du, dv, dw, g, r0, h[0], h[1], h[2], eps_smooth, eps_data, phi,
-                         fuse ? nullptr : ksi, st));
-  float *a0 = du, *a1 = dv, *a2 = dw, *b0 = tdu, *b1 = tdv, *b2 = tdw;
-  for (size_t j = 1; j <= inner; ++j) {
-    ZRange r{lo_face ? r0.begin : r0.begin + (int)j, hi_face ? r0.end : r0.end - (int)j};
-    F3D_TRY(launch_sweep(fx, fy, fz, ft, u, v, w, a0, a1, a2, phi, ksi, g, r, h[0], h[1], h[2], alpha, b0, b1, b2,
-                         st, (fuse && j == 1) ? ksi : nullptr, eps_data));
-    std::swap(a0, b0);
-    std::swap(a1, b1);
-    std::swap(a2, b2);
-  }
-  *result_in_tmp = (a0 == tdu) ? 1 : 0;
-  return FLOW3D_OK;
+  return outer_iteration_parts(fx, fy, fz, ft, u, v, w, du, dv, dw, tdu, tdv, tdw, phi, ksi, g, make_range(g, slab), h,
+                               inner, alpha, eps_smooth, eps_data, 0, 0, 0, result_in_tmp, S(stream));
+}
+
+int flow3d_outer_iteration_slab_part(const float* fx, const float* fy, const float* fz, const float* ft,
+                                     const float* u, const float* v, const float* w, float* du, float* dv,
+                                     float* dw, float* tdu, float* tdv, float* tdw, float* phi, float* ksi,
+                                     const size_t dims[3], size_t ld, const flow3d_zslab* slab,
+                                     const float h[3], size_t inner, float alpha, float eps_smooth,
+                                     float eps_data, int part, size_t own_begin, size_t own_end,
+                                     int* result_in_tmp, void* stream) {
+  const void* ps[] = {fx, fy, fz, ft, u, v, w, du, dv, dw, tdu, tdv, tdw, phi, ksi};
+  for (const void* p : ps) F3D_TRY(check_volume(p, dims, ld));
+  F3D_TRY(check_slab(dims, slab));
+  if (!h || !slab || !result_in_tmp || part < 0 || part > 2) return FLOW3D_ERR_INVALID_ARG;
+  if (own_begin > own_end || own_end > dims[2]) return FLOW3D_ERR_INVALID_ARG;
+  const Dims g = make_slab_dims(dims, ld, slab);
+  return outer_iteration_parts(fx, fy, fz, ft, u, v, w, du, dv, dw, tdu, tdv, tdw, phi, ksi, g, make_range(g, slab), h,
+                               inner, alpha, eps_smooth, eps_data, part, (int)own_begin, (int)own_end, result_in_tmp,
+                               S(stream));
 }
 
 int flow3d_median_slab(const float* in, float* out, const size_t dims[3], size_t ld,

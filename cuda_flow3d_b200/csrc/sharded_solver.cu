@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -104,6 +105,14 @@ struct flow3d_sharded {
   cudaStream_t st = nullptr;  // stream of the running compute call
   float* scalar_dev = nullptr;
   float* scalar_host = nullptr;  // pinned
+  // overlapped ghost exchange: NCCL runs on its own stream, ordered against the solve's stream by events
+  cudaStream_t comm_st = nullptr;
+  cudaEvent_t ev_pack = nullptr, ev_comm = nullptr;
+  bool overlap = true;
+  bool use_arena = true;
+  bool log = false;
+  int log_level = 0;
+  double log_t = 0;
   // memory: stream-ordered pool, nothing is returned to the OS between solves
   size_t live_bytes = 0, peak_bytes = 0;
   std::map<float*, size_t> sizes;
@@ -118,10 +127,48 @@ struct flow3d_sharded {
   size_t tuned_levels = 0, tuned_inner = 0;
   size_t min_planes = 12, min_voxels = (size_t)1 << 18;
 
+  // Device memory of a solve.  The FIRST solve allocates through the stream-ordered pool and records its
+  // high-water mark; after it one arena of that size (+25 %) is allocated and every later solve carves its
+  // buffers out of it with a first-fit free list on the host: no driver call in the hot path (the pool was
+  // measured to block the host for 100-300 ms per large level while it re-mapped memory), and the same
+  // deterministic layout every solve.  Reuse of a freed block is safe without events: all work is ordered
+  // on the solve's stream, and the communication stream is joined before anything it touched is released.
+  // A request the arena cannot place (fragmentation, larger reach) falls back to the pool.
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  std::map<size_t, size_t> arena_free;  // offset -> size
+  size_t pool_peak = 0;                 // high-water mark of a solve that ran without the arena
+  float* arena_take(size_t bytes) {
+    bytes = (bytes + 511) & ~(size_t)511;
+    for (auto it = arena_free.begin(); it != arena_free.end(); ++it) {
+      if (it->second < bytes) continue;
+      const size_t off = it->first, rest = it->second - bytes;
+      arena_free.erase(it);
+      if (rest) arena_free[off + bytes] = rest;
+      return reinterpret_cast<float*>(arena + off);
+    }
+    return nullptr;
+  }
+  void arena_give(float* p, size_t bytes) {
+    bytes = (bytes + 511) & ~(size_t)511;
+    size_t off = (size_t)(reinterpret_cast<char*>(p) - arena);
+    auto next = arena_free.lower_bound(off);
+    if (next != arena_free.begin()) {
+      auto prev = std::prev(next);
+      if (prev->first + prev->second == off) { off = prev->first; bytes += prev->second; arena_free.erase(prev); }
+    }
+    if (next != arena_free.end() && off + bytes == next->first) { bytes += next->second; arena_free.erase(next); }
+    arena_free[off] = bytes;
+  }
+  bool in_arena(const float* p) const {
+    const char* c = reinterpret_cast<const char*>(p);
+    return arena && c >= arena && c < arena + arena_bytes;
+  }
   int alloc(size_t floats, float** out) {
     if (floats == 0) floats = 4;
     const size_t bytes = floats * sizeof(float);
-    M_CUDA(cudaMallocAsync(reinterpret_cast<void**>(out), bytes, st));
+    *out = arena ? arena_take(bytes) : nullptr;
+    if (!*out) M_CUDA(cudaMallocAsync(reinterpret_cast<void**>(out), bytes, st));
     sizes[*out] = bytes;
     live_bytes += bytes;
     peak_bytes = std::max(peak_bytes, live_bytes);
@@ -137,10 +184,16 @@ struct flow3d_sharded {
     auto it = sizes.find(p);
     if (it == sizes.end()) return;
     live_bytes -= it->second;
+    if (in_arena(p)) arena_give(p, it->second);
+    else cudaFreeAsync(p, st);
     sizes.erase(it);
-    cudaFreeAsync(p, st);
   }
+  double host_now() const {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  }
+  std::vector<std::pair<int, double>> host_marks;  // log mode: host clock at every phase mark
   void mark(int phase) {
+    if (log) host_marks.emplace_back(phase, host_now());
     if (!profiling) return;
     if (events_used == event_pool.size()) {
       cudaEvent_t e;
@@ -196,6 +249,43 @@ int exchange(flow3d_sharded* s, float* const* fields, int nf, size_t plane, size
     }
   }
   M_NCCL(ncclGroupEnd());
+  s->stats[2] += 1;
+  s->stats[3] += (double)nf * ((lo ? nsend : 0) + (hi ? nsend : 0)) * plane * sizeof(float);
+  return FLOW3D_OK;
+}
+
+// The same exchange, overlappable: the boundary planes are first copied into `sendbuf` on the solve's
+// stream (the next iteration's early sweeps overwrite them), then the NCCL group runs on the communication
+// stream: sends from the copy, receives straight into the ghost planes.  The caller makes the solve's stream
+// wait for ev_comm before anything touches the ghosts.
+int exchange_async(flow3d_sharded* s, float* const* fields, int nf, size_t plane, size_t A, size_t B, size_t a, size_t b,
+                   size_t Hg, float* sendbuf) {
+  const bool lo = s->rank > 0 && a > A, hi = s->rank < s->world - 1 && B > b;
+  if (!lo && !hi) return FLOW3D_OK;
+  const size_t nsend = std::min(Hg, b - a), chunk = nsend * plane;
+  for (int f = 0; f < nf; ++f) {
+    if (lo)
+      M_CUDA(cudaMemcpyAsync(sendbuf + (size_t)(2 * f) * chunk, fields[f] + (a - A) * plane, chunk * sizeof(float),
+                             cudaMemcpyDeviceToDevice, s->st));
+    if (hi)
+      M_CUDA(cudaMemcpyAsync(sendbuf + (size_t)(2 * f + 1) * chunk, fields[f] + (b - A - nsend) * plane,
+                             chunk * sizeof(float), cudaMemcpyDeviceToDevice, s->st));
+  }
+  M_CUDA(cudaEventRecord(s->ev_pack, s->st));
+  M_CUDA(cudaStreamWaitEvent(s->comm_st, s->ev_pack, 0));
+  M_NCCL(ncclGroupStart());
+  for (int f = 0; f < nf; ++f) {
+    if (lo) {
+      M_NCCL(ncclRecv(fields[f], (a - A) * plane, ncclFloat, s->rank - 1, s->comm, s->comm_st));
+      M_NCCL(ncclSend(sendbuf + (size_t)(2 * f) * chunk, chunk, ncclFloat, s->rank - 1, s->comm, s->comm_st));
+    }
+    if (hi) {
+      M_NCCL(ncclSend(sendbuf + (size_t)(2 * f + 1) * chunk, chunk, ncclFloat, s->rank + 1, s->comm, s->comm_st));
+      M_NCCL(ncclRecv(fields[f] + (b - A) * plane, (B - b) * plane, ncclFloat, s->rank + 1, s->comm, s->comm_st));
+    }
+  }
+  M_NCCL(ncclGroupEnd());
+  M_CUDA(cudaEventRecord(s->ev_comm, s->comm_st));
   s->stats[2] += 1;
   s->stats[3] += (double)nf * ((lo ? nsend : 0) + (hi ? nsend : 0)) * plane * sizeof(float);
   return FLOW3D_OK;
@@ -452,23 +542,58 @@ int solve(flow3d_sharded* s, Frames& frames, const flow3d_params* P, float* out_
     }
     M_TRY(s->zeros(dl * plane, &phi));
     M_TRY(s->zeros(dl * plane, &ksi));
-    for (size_t it = 0; it < outer; ++it) {
-      s->mark(FLOW3D_MGPU_PHASE_SOLVER);
-      int in_tmp = 0;
-      M_TRY(flow3d_outer_iteration_slab(terms[0], terms[1], terms[2], terms[3], flow[0].p, flow[1].p, flow[2].p, dc[0],
-                                        dc[1], dc[2], da[0], da[1], da[2], phi, ksi, dims_l, ldl, &sl1, L.h, inner,
-                                        P->equation_alpha, P->equation_smoothness, P->equation_data, &in_tmp, s->st));
-      if (in_tmp)
-        for (int c = 0; c < 3; ++c) std::swap(dc[c], da[c]);
+    // Sharded levels overlap the ghost exchange with compute: the exchange that follows iteration i runs on
+    // the communication stream while the EARLY part of iteration i+1 (every plane that cannot depend on the
+    // ghosts: ~95 % of the work) runs on the solve's stream; the LATE part waits for it.
+    const bool ovl = sharded && s->overlap && (b - a) >= 4 * Hg;
+    float* sendbuf = nullptr;
+    if (ovl) M_TRY(s->alloc(6 * Hg * plane, &sendbuf));
+    bool pending = false;  // an exchange into dc's ghosts is in flight on the communication stream
+    auto count_units = [&]() {
       for (size_t j = 1; j <= inner; ++j)
         s->stats[5] += (double)w * hh * (double)((hi1 == d ? hi1 : hi1 - j) - (lo1 == 0 ? lo1 : lo1 + j));
       s->stats[6] += (double)w * hh * (double)(hi1 - lo1);
+    };
+    for (size_t it = 0; it < outer; ++it) {
+      s->mark(FLOW3D_MGPU_PHASE_SOLVER);
+      int in_tmp = 0;
+      if (!pending) {
+        M_TRY(flow3d_outer_iteration_slab(terms[0], terms[1], terms[2], terms[3], flow[0].p, flow[1].p, flow[2].p, dc[0],
+                                          dc[1], dc[2], da[0], da[1], da[2], phi, ksi, dims_l, ldl, &sl1, L.h, inner,
+                                          P->equation_alpha, P->equation_smoothness, P->equation_data, &in_tmp, s->st));
+      } else {
+        M_TRY(flow3d_outer_iteration_slab_part(terms[0], terms[1], terms[2], terms[3], flow[0].p, flow[1].p, flow[2].p,
+                                               dc[0], dc[1], dc[2], da[0], da[1], da[2], phi, ksi, dims_l, ldl, &sl1, L.h,
+                                               inner, P->equation_alpha, P->equation_smoothness, P->equation_data, 1,
+                                               a - A, b - A, &in_tmp, s->st));
+        s->mark(FLOW3D_MGPU_PHASE_HALO_EXCHANGE);  // what is left of the exchange after the early part
+        M_CUDA(cudaStreamWaitEvent(s->st, s->ev_comm, 0));
+        s->mark(FLOW3D_MGPU_PHASE_SOLVER);
+        pending = false;
+        M_TRY(flow3d_outer_iteration_slab_part(terms[0], terms[1], terms[2], terms[3], flow[0].p, flow[1].p, flow[2].p,
+                                               dc[0], dc[1], dc[2], da[0], da[1], da[2], phi, ksi, dims_l, ldl, &sl1, L.h,
+                                               inner, P->equation_alpha, P->equation_smoothness, P->equation_data, 2,
+                                               a - A, b - A, &in_tmp, s->st));
+      }
+      if (in_tmp)
+        for (int c = 0; c < 3; ++c) std::swap(dc[c], da[c]);
+      count_units();
       if (sharded) {
-        s->mark(FLOW3D_MGPU_PHASE_HALO_EXCHANGE);
-        M_TRY(exchange(s, dc, 3, plane, A, B, a, b, Hg));
+        if (ovl) {
+          M_TRY(exchange_async(s, dc, 3, plane, A, B, a, b, Hg, sendbuf));
+          pending = true;
+        } else {
+          s->mark(FLOW3D_MGPU_PHASE_HALO_EXCHANGE);
+          M_TRY(exchange(s, dc, 3, plane, A, B, a, b, Hg));
+        }
       }
     }
+    if (pending) {  // the update, the median and the next prolongation read the iterate's ghost planes
+      s->mark(FLOW3D_MGPU_PHASE_HALO_EXCHANGE);
+      M_CUDA(cudaStreamWaitEvent(s->st, s->ev_comm, 0));
+    }
     s->mark(FLOW3D_MGPU_PHASE_UPDATE);
+    s->release(sendbuf);
     for (int i = 0; i < 4; ++i) s->release(terms[i]);
     s->release(phi);
     s->release(ksi);
@@ -492,6 +617,21 @@ int solve(flow3d_sharded* s, Frames& frames, const flow3d_params* P, float* out_
     pv_lo = m_lo; pv_hi = m_hi;
     have_prev = true;
     s->mark(-1);
+    if (s->log) {  // FLOW3D_MGPU_LOG=1: host clock per level (synchronising; 2 = not synchronising; debugging aid)
+      if (s->log_level == 1) cudaStreamSynchronize(s->st);
+      const double now = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+      double host_ms[FLOW3D_MGPU_PHASE_COUNT] = {0};  // host time spent ENQUEUING each phase
+      for (size_t i = 0; i + 1 < s->host_marks.size(); ++i)
+        if (s->host_marks[i].first >= 0)
+          host_ms[s->host_marks[i].first] += (s->host_marks[i + 1].second - s->host_marks[i].second) * 1e3;
+      s->host_marks.clear();
+      std::fprintf(stderr, "[flow3d mgpu r%d] level %d %zux%zux%zu %s [%zu,%zu): %.1f ms since previous; host enqueue ms: "
+                   "prol %.1f xchg %.1f frames %.1f warp %.1f solver %.1f halo %.1f upd %.1f med %.1f; pool live %.2f GB\n",
+                   s->rank, L.level, w, hh, d, sharded ? (ovl ? "sharded+overlap" : "sharded") : "replicated", a, b,
+                   s->log_t > 0 ? (now - s->log_t) * 1e3 : 0.0, host_ms[0], host_ms[1], host_ms[2], host_ms[3], host_ms[4],
+                   host_ms[5], host_ms[6], host_ms[7], s->live_bytes / 1e9);
+      s->log_t = now;
+    }
   }
   // ---- this rank's owned planes of the finest level ---------------------------------------------------------
   if (b - a > out_capacity) return FLOW3D_ERR_INVALID_ARG;
@@ -573,6 +713,18 @@ int flow3d_sharded_create(size_t width, size_t height, size_t depth, int device,
     flow3d_sharded_destroy(s);
     return FLOW3D_ERR_OUT_OF_MEMORY;
   }
+  // highest priority: the exchange's copy kernels must get SM slots while a sweep's grid is still draining
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (cudaStreamCreateWithPriority(&s->comm_st, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+      cudaEventCreateWithFlags(&s->ev_pack, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&s->ev_comm, cudaEventDisableTiming) != cudaSuccess) {
+    flow3d_sharded_destroy(s);
+    return FLOW3D_ERR_CUDA;
+  }
+  if (const char* e = getenv("FLOW3D_MGPU_OVERLAP")) s->overlap = std::atoi(e) != 0;
+  if (const char* e = getenv("FLOW3D_MGPU_ARENA")) s->use_arena = std::atoi(e) != 0;
+  if (const char* e = getenv("FLOW3D_MGPU_LOG")) { s->log_level = std::atoi(e); s->log = s->log_level != 0; }
   if (world > 1) {
     ncclUniqueId id;
     std::memcpy(&id, id128, sizeof(id));
@@ -596,7 +748,11 @@ int flow3d_sharded_destroy(flow3d_sharded* s) {
   cudaSetDevice(s->device);
   cudaDeviceSynchronize();
   if (s->comm) ncclCommDestroy(s->comm);
+  if (s->ev_pack) cudaEventDestroy(s->ev_pack);
+  if (s->ev_comm) cudaEventDestroy(s->ev_comm);
+  if (s->comm_st) cudaStreamDestroy(s->comm_st);
   for (cudaEvent_t e : s->event_pool) cudaEventDestroy(e);
+  if (s->arena) cudaFree(s->arena);
   if (s->scalar_dev) cudaFree(s->scalar_dev);
   if (s->scalar_host) cudaFreeHost(s->scalar_host);
   delete s;
@@ -649,7 +805,7 @@ int flow3d_sharded_stats(flow3d_sharded* s, double out[8]) {
   if (!s) return FLOW3D_ERR_NOT_INITIALIZED;
   if (!out) return FLOW3D_ERR_INVALID_ARG;
   for (int i = 0; i < 7; ++i) out[i] = s->stats[i];
-  out[7] = (double)s->peak_bytes;
+  out[7] = (double)(s->arena ? s->arena_bytes : s->peak_bytes);
   return FLOW3D_OK;
 }
 
@@ -712,6 +868,23 @@ int flow3d_sharded_compute(flow3d_sharded* s, const float* raw_0, const float* r
   if (rc == FLOW3D_OK) rc = solve(s, frames, params, flow_u, flow_v, flow_w, ld, out_capacity_planes, out_a, out_b);
   frames.destroy();
   s->mark(-1);
+  if (rc == FLOW3D_OK && !s->arena && s->use_arena) {  // first solve done: fix the memory layout for the next ones
+    s->pool_peak = s->peak_bytes;
+    const size_t want = s->pool_peak + s->pool_peak / 4 + ((size_t)64 << 20);
+    cudaStreamSynchronize(s->st);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, s->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);  // hand the pool's memory over
+    void* p = nullptr;
+    if (cudaMalloc(&p, want) == cudaSuccess) {
+      s->arena = static_cast<char*>(p);
+      s->arena_bytes = want;
+      s->arena_free.clear();
+      s->arena_free[0] = want;
+    } else {
+      cudaGetLastError();
+      s->use_arena = false;  // not enough room for pool + arena: stay on the pool
+    }
+  }
   if (rc != FLOW3D_OK) {  // drop whatever a failed level left behind
     std::vector<float*> left;
     for (auto& kv : s->sizes) left.push_back(kv.first);

@@ -224,6 +224,20 @@ int flow3d_outer_iteration_slab(const float* fx, const float* fy, const float* f
                                 const size_t dims[3], size_t ld, const flow3d_zslab* slab,
                                 const float h[3], size_t inner, float alpha, float eps_smooth,
                                 float eps_data, int* result_in_tmp, void* stream);
+/* The same outer iteration split for communication overlap.  [own_begin, own_end) = the local planes this
+ * rank owns (the rest of [z_begin, z_end) are ghost planes filled by a neighbour exchange).  part 1
+ * ("early") runs, for phi and every sweep, only the planes whose values cannot depend on the ghosts
+ * (step j on [own_begin+j+1, own_end-j-1), extended to a global face where there is one): it may start
+ * before the ghosts of the starting iterate have arrived.  part 2 ("late") runs the remaining planes of
+ * every step and must follow part 1 and the exchange.  part 1 + part 2 = part 0 = flow3d_outer_iteration_slab,
+ * bit for bit; early and late launches touch disjoint planes of every buffer at every step. */
+int flow3d_outer_iteration_slab_part(const float* fx, const float* fy, const float* fz, const float* ft,
+                                     const float* u, const float* v, const float* w, float* du, float* dv,
+                                     float* dw, float* tdu, float* tdv, float* tdw, float* phi, float* ksi,
+                                     const size_t dims[3], size_t ld, const flow3d_zslab* slab,
+                                     const float h[3], size_t inner, float alpha, float eps_smooth,
+                                     float eps_data, int part, size_t own_begin, size_t own_end,
+                                     int* result_in_tmp, void* stream);
 int flow3d_median_slab(const float* in, float* out, const size_t dims[3], size_t ld,
                        const flow3d_zslab* slab, size_t radius, void* stream);
 /* resample with the input and the output each given as a slab of its level; x and y passes run on

@@ -117,3 +117,62 @@ def test_absmax(gpu):
     out = gpu.DeviceVolume.zeros((4, 1, 1))
     check(L.flow3d_absmax(v.ptr, sz3(v.dims), v.ld, out.ptr, None), "absmax")
     assert out.numpy().ravel()[0] == np.abs(a).max()
+
+
+@pytest.mark.parametrize("case", [(40, 13, 21, 6, 30), (40, 13, 21, 0, 26), (44, 20, 70, 14, 44)])
+def test_outer_iteration_early_late_split(gpu, case):
+    """flow3d_outer_iteration_slab_part: early + late = the unsplit iteration bit for bit, and the EARLY part
+    must not read the ghost planes at all: it runs with the ghosts of the starting iterate poisoned (NaN),
+    the ghosts are restored (the "exchange arrives"), then the late part runs."""
+    from cuda_flow3d_b200._lib import ZSlab, check, f3, load, sz3
+    L = load()
+    d, h, w, a, b = case  # level depth; this rank owns global planes [a, b)
+    H = 6
+    A, B = max(0, a - H), min(d, b + H)
+    hh = (1.05, 1.1, 1.25)
+    shape = (d, h, w)
+    f0, f1w = smooth_volume(shape, 6), smooth_volume(shape, 7)
+    u, v, ww = random_fields(shape, 8, 3, 2.0)
+    du, dv, dw = random_fields(shape, 9, 3, 0.2)
+    fx, fy, fz, ft = gpu.ops.derivatives(f0, f1w, hh)
+    sl = lambda x: np.ascontiguousarray(x[A:B])
+    dims = sz3((w, h, B - A))
+    lo1 = A if A == 0 else A + 1
+    hi1 = B if B == d else B - 1
+    slab = ZSlab(A, d, lo1 - A, hi1 - A)
+
+    def run(parts, poison):
+        st = [_dv(gpu, sl(x)) for x in (fx, fy, fz, ft, u, v, ww)]
+        cur = [sl(x).copy() for x in (du, dv, dw)]
+        good = [c.copy() for c in cur]
+        if poison:
+            for c in cur:
+                c[:a - A] = np.nan
+                c[b - A:] = np.nan
+        dcur = [_dv(gpu, c) for c in cur]
+        dalt = [gpu.DeviceVolume.zeros((w, h, B - A)) for _ in range(3)]
+        phi, ksi = gpu.DeviceVolume.zeros((w, h, B - A)), gpu.DeviceVolume.zeros((w, h, B - A))
+        flag = C.c_int(0)
+        for part in parts:
+            if part == 2 and poison:  # the exchange arrives: ghosts of the starting iterate become valid
+                for t, gd in zip(dcur, good):
+                    fixed = t.numpy()
+                    fixed[:a - A] = gd[:a - A]
+                    fixed[b - A:] = gd[b - A:]
+                    check(L.flow3d_upload(fixed.ctypes.data_as(C.c_void_p), t.ptr, dims, t.ld, None), "upload")
+                    check(L.flow3d_stream_synchronize(None), "sync")
+            check(L.flow3d_outer_iteration_slab_part(*[t.ptr for t in st], *[t.ptr for t in dcur], *[t.ptr for t in dalt],
+                                                     phi.ptr, ksi.ptr, dims, st[0].ld, C.byref(slab), f3(hh), 5, 7.5, 0.001,
+                                                     0.001, part, a - A, b - A, C.byref(flag), None), "outer_iteration_part")
+        res = dalt if flag.value else dcur
+        return [t.numpy() for t in res], phi.numpy(), ksi.numpy()
+
+    ref, ref_phi, ref_ksi = run([0], False)
+    got, got_phi, got_ksi = run([1, 2], True)
+    # valid after 5 sweeps: everything at least H-1 planes away from a non-face buffer end
+    v_lo = 0 if A == 0 else 6
+    v_hi = (B - A) if B == d else (B - A) - 6
+    for c in range(3):
+        assert np.array_equal(got[c][v_lo:v_hi], ref[c][v_lo:v_hi])
+        assert not np.isnan(got[c][v_lo:v_hi]).any()
+    assert np.array_equal(got_phi[lo1 - A:hi1 - A], ref_phi[lo1 - A:hi1 - A])
