@@ -34,7 +34,7 @@ $(PKG)/host/%.o: $(PKG)/host/%.cpp
 	$(HOSTCXX) -std=c++17 -O2 -fPIC -fno-fast-math -Iinclude -I$(PKG)/host -c $< -o $@
 
 $(LIB): $(CU_OBJS) $(HOST_OBJS)
-	$(NVCC) $(ARCH) -ccbin $(HOSTCXX) -shared -o $@ $^
+	$(NVCC) $(ARCH) -ccbin $(HOSTCXX) -shared -o $@ $^ -ldl
 
 # multi-GPU: the z-sharded solver (host C++ over the C ABI above + NCCL); a separate library so that the
 # single-GPU library carries no NCCL dependency

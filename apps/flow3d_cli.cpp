@@ -2,7 +2,7 @@
 // main.cpp is a lab script with hard-coded dims and paths; this is the real CLI).
 //
 //   flow3d_cli --dims W H D --frame0 a.raw --frame1 b.raw [--f32] [--out prefix] [--vtk file.vtk]
-//              [--param key=value ...] [--reps N] [--device k] [--verbose]
+//              [--param key=value ...] [--reps N] [--device k | --gpus N] [--verbose]
 //              [--diagnostics] [--tolerance T] [--warped PREFIX]
 //   flow3d_cli --pairs "frames_%04d.raw" FIRST LAST ...   consecutive frame pairs, solver kept alive
 #include <chrono>
@@ -21,9 +21,10 @@ namespace {
 void usage(const char* a0) {
   std::printf(
       "usage: %s --dims W H D --frame0 F0 --frame1 F1 [--f32] [--out PREFIX] [--vtk FILE]\n"
-      "          [--param key=value]... [--reps N] [--device K] [--verbose]\n"
+      "          [--param key=value]... [--reps N] [--device K | --gpus N] [--verbose]\n"
       "          [--diagnostics] [--tolerance T] [--warped PREFIX]\n"
       "       %s --dims W H D --pairs PATTERN FIRST LAST [--f32] [--out PREFIX] ...\n"
+      "--gpus N z-shards the volume over devices 0..N-1 (NCCL halo exchange; same bits as one GPU).\n"
       "--diagnostics prints the Jacobi update norm per level; --tolerance T stops a level once the RMS\n"
       "update falls below T voxels (not the reference's fixed iteration count); --warped writes the\n"
       "registered frame 1 (PREFIX_warped.raw) and |warped - frame0| (PREFIX_error.raw), float32.\n"
@@ -60,7 +61,7 @@ int main(int argc, char** argv) {
   float tolerance = 0.f;
   long first = 0, last = -1;
   bool f32 = false, verbose = false;
-  int reps = 1, device = 0;
+  int reps = 1, device = 0, gpus = 1;
   flow3d_params p;
   flow3d_default_params(&p);
   for (int i = 1; i < argc; ++i) {
@@ -79,6 +80,7 @@ int main(int argc, char** argv) {
     else if (a == "--verbose") verbose = true;
     else if (a == "--reps" && need(1)) reps = std::atoi(argv[++i]);
     else if (a == "--device" && need(1)) device = std::atoi(argv[++i]);
+    else if (a == "--gpus" && need(1)) gpus = std::atoi(argv[++i]);
     else if (a == "--param" && need(1)) { if (!set_param(p, argv[++i])) { std::printf("bad --param %s\n", argv[i]); return 2; } }
     else { usage(argv[0]); return 2; }
   }
@@ -99,6 +101,12 @@ int main(int argc, char** argv) {
   if (!InitCudaContextWithFirstAvailableDevice(&ctx)) return 1;
   OpticalFlowE solver;
   solver.SetDevice(device);
+  if (gpus > 1) {
+    std::vector<int> devs;
+    for (int d = 0; d < gpus; ++d) devs.push_back(d);
+    solver.SetDevices(devs);
+    if (diagnostics) { std::printf("--diagnostics is single-GPU only\n"); return 2; }
+  }
   solver.silent = !verbose;
   DataSize4 size = {W, H, D, 0};
   if (!solver.Initialize(size)) return 1;

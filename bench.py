@@ -332,6 +332,10 @@ def run_sharded(args, rank, world, local_rank):
     send/recv of the ghost planes per outer iteration, on the solve's stream).  torch.distributed is only
     the launcher-side plumbing here: it hands out the NCCL id and reduces the timings."""
     import hashlib
+    # more NCCL channels per send/recv peer (see csrc/sharded_solver.cu); set before any NCCL initialisation in
+    # this process because NCCL reads its parameters once
+    for k, v in (("NCCL_NCHANNELS_PER_PEER", "32"), ("NCCL_MIN_P2P_NCHANNELS", "32"), ("NCCL_MAX_P2P_NCHANNELS", "64")):
+        os.environ.setdefault(k, v)
     import torch
     import torch.distributed as dist
     import cuda_flow3d_b200 as pkg

@@ -115,6 +115,7 @@ SIGNATURES = {
     "flow3d_tune_query": (C.c_int, [C.c_int, _sz3, C.c_size_t, C.POINTER(ZSlab), C.c_int * 3]),
     "flow3d_solver_last_timing": (C.c_int, [_vp, C.c_float * 2]),
     "flow3d_solver_set_profiling": (C.c_int, [_vp, C.c_int]),
+    "flow3d_solver_set_verbose": (C.c_int, [_vp, C.c_int]),
     "flow3d_solver_stage_times": (C.c_int, [_vp, C.c_float * 8, C.c_double * 8, C.c_uint64 * 8]),
     "flow3d_solver_set_level_callback": (C.c_int, [_vp, LEVEL_CALLBACK, _vp]),
     "flow3d_update_norm_workspace_bytes": (C.c_size_t, []),

@@ -272,6 +272,7 @@ struct flow3d_solver {
   std::vector<size_t> diag_level_outer;  // outer iterations run per level, coarsest first
   std::vector<double> diag_records;      // {sum_sq, max_abs} per outer iteration, levels concatenated
   std::vector<double> diag_level_voxels;
+  bool verbose = false;  // print the reference's per-level line (optical_flow_e.cpp:270-271)
   // launch shapes tuned for this (scale factor, level count)?  (flow3d_solver_tune)
   float tuned_scale = -1.f;
   size_t tuned_levels = 0;
@@ -345,6 +346,8 @@ static int run_pyramid(flow3d_solver* s, const float* in0, const float* in1, siz
     const size_t ld = aligned_ld(cur[0]);
     const Dims g = make_dims(cur, ld);
     const size_t bytes = (size_t)g.ps * g.d * sizeof(float);
+    if (s->verbose)  // the reference's own line, printed as the level is enqueued (the device runs behind)
+      std::printf("Solve level %2d (%4d x%4d x%4d) \n", level, (int)cur[0], (int)cur[1], (int)cur[2]);
 
     const double nvox = (double)cur[0] * cur[1] * cur[2];
     tm->mark(FLOW3D_STAGE_RESAMPLE, st, 5.0 * nvox);
@@ -987,6 +990,12 @@ int flow3d_solver_compute_host(flow3d_solver* s, const float* frame_0, const flo
   s->timer.finish();
   F3D_CUDA(cudaEventElapsedTime(&s->last_ms[0], s->ev[0], s->ev[1]));
   F3D_CUDA(cudaEventElapsedTime(&s->last_ms[1], s->ev[2], s->ev[3]));
+  return FLOW3D_OK;
+}
+
+int flow3d_solver_set_verbose(flow3d_solver* s, int enable) {
+  if (!s) return FLOW3D_ERR_NOT_INITIALIZED;
+  s->verbose = enable != 0;
   return FLOW3D_OK;
 }
 

@@ -804,7 +804,11 @@ int launch_sweep(const float* fx, const float* fy, const float* fz, const float*
               zr.begin, zr.end, 32, 0, 1, ksi_out, eps_d};
   TuneCfg cfg = static_sweep_cfg(g, zr);
   static const int forced_vec = env_int("FLOW3D_SWEEP_VEC", 0), forced_variant = env_int("FLOW3D_SWEEP_VARIANT", -1);
-  if (forced_vec == 0 && forced_variant < 0) tune_lookup(tune_key(ksi_out ? TK_SWEEP_KSI : TK_SWEEP, g, zr), &cfg);
+  // a short range inside a deep slab (the "late" launches of the overlapped multi-GPU iteration: a few
+  // ghost-dependent planes) must not inherit the slab's chunk count: static shape, one chunk
+  const bool short_part = (zr.end - zr.begin) * 2 < g.d;
+  if (forced_vec == 0 && forced_variant < 0 && !short_part)
+    tune_lookup(tune_key(ksi_out ? TK_SWEEP_KSI : TK_SWEEP, g, zr), &cfg);
   const int rc = launch_sweep_cfg(a, g, zr, cfg, st);
   if (rc == FLOW3D_ERR_UNSUPPORTED && sweep_variant_is_tma(cfg.variant))  // no TMA entry point in this driver
     return launch_sweep_cfg(a, g, zr, TuneCfg{pick_vec(g), 0, SWEEP_VARIANT_REG}, st);
@@ -1046,7 +1050,7 @@ int launch_phi_ksi(const float* fx, const float* fy, const float* fz, const floa
   PhiKsiArgs a{fx, fy, fz, ft, u, v, w, du, dv, dw, phi, ksi, g, hx, hy, hz, eps_s, eps_d};
   static const int forced = env_int("FLOW3D_PHIKSI_VEC", 0);
   TuneCfg cfg{static_phi_vec(g), 0, 0};
-  if (forced == 0) tune_lookup(tune_key(ksi ? TK_PHI_KSI : TK_PHI, g, zr), &cfg);
+  if (forced == 0 && (zr.end - zr.begin) * 2 >= g.d) tune_lookup(tune_key(ksi ? TK_PHI_KSI : TK_PHI, g, zr), &cfg);
   return launch_phi_ksi_cfg(a, g, zr, cfg, st);
 }
 

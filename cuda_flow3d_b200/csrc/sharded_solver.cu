@@ -109,6 +109,7 @@ struct flow3d_sharded {
   cudaStream_t comm_st = nullptr;
   cudaEvent_t ev_pack = nullptr, ev_comm = nullptr;
   bool overlap = true;
+  size_t overlap_min_plane = 360000;  // voxels per plane from which the overlapped exchange is used
   bool use_arena = true;
   bool log = false;
   int log_level = 0;
@@ -128,7 +129,7 @@ struct flow3d_sharded {
   size_t min_planes = 12, min_voxels = (size_t)1 << 18;
 
   // Device memory of a solve.  The FIRST solve allocates through the stream-ordered pool and records its
-  // high-water mark; after it one arena of that size (+25 %) is allocated and every later solve carves its
+  // high-water mark; after it one arena of that size (+10 %) is allocated and every later solve carves its
   // buffers out of it with a first-fit free list on the host: no driver call in the hot path (the pool was
   // measured to block the host for 100-300 ms per large level while it re-mapped memory), and the same
   // deterministic layout every solve.  Reuse of a freed block is safe without events: all work is ordered
@@ -545,7 +546,10 @@ int solve(flow3d_sharded* s, Frames& frames, const flow3d_params* P, float* out_
     // Sharded levels overlap the ghost exchange with compute: the exchange that follows iteration i runs on
     // the communication stream while the EARLY part of iteration i+1 (every plane that cannot depend on the
     // ghosts: ~95 % of the work) runs on the solve's stream; the LATE part waits for it.
-    const bool ovl = sharded && s->overlap && (b - a) >= 4 * Hg;
+    // Splitting costs ~12 extra small launches per iteration (~0.1 ms); the exchange costs latency + bytes /
+    // ~150 GB/s (NCCL send/recv between two peers).  Measured on B200s: a wash at 512^2 planes, a win from
+    // ~600^2 on -- smaller levels keep the serial exchange on the solve's stream.
+    const bool ovl = sharded && s->overlap && (b - a) >= 4 * Hg && w * hh >= s->overlap_min_plane;
     float* sendbuf = nullptr;
     if (ovl) M_TRY(s->alloc(6 * Hg * plane, &sendbuf));
     bool pending = false;  // an exchange into dc's ghosts is in flight on the communication stream
@@ -723,9 +727,15 @@ int flow3d_sharded_create(size_t width, size_t height, size_t depth, int device,
     return FLOW3D_ERR_CUDA;
   }
   if (const char* e = getenv("FLOW3D_MGPU_OVERLAP")) s->overlap = std::atoi(e) != 0;
+  if (const char* e = getenv("FLOW3D_MGPU_OVERLAP_MIN_PLANE")) s->overlap_min_plane = std::strtoull(e, nullptr, 10);
   if (const char* e = getenv("FLOW3D_MGPU_ARENA")) s->use_arena = std::atoi(e) != 0;
   if (const char* e = getenv("FLOW3D_MGPU_LOG")) { s->log_level = std::atoi(e); s->log = s->log_level != 0; }
   if (world > 1) {
+    // NCCL's send/recv between two peers defaults to 2 channels (~55 GB/s per direction measured on B200 /
+    // NVLink 5); more channels per peer raise it ~1.6x.  Only defaults: an explicit setting wins.
+    setenv("NCCL_NCHANNELS_PER_PEER", "32", 0);
+    setenv("NCCL_MIN_P2P_NCHANNELS", "32", 0);
+    setenv("NCCL_MAX_P2P_NCHANNELS", "64", 0);
     ncclUniqueId id;
     std::memcpy(&id, id128, sizeof(id));
     const ncclResult_t r = ncclCommInitRank(&s->comm, world, id, rank);
@@ -870,7 +880,7 @@ int flow3d_sharded_compute(flow3d_sharded* s, const float* raw_0, const float* r
   s->mark(-1);
   if (rc == FLOW3D_OK && !s->arena && s->use_arena) {  // first solve done: fix the memory layout for the next ones
     s->pool_peak = s->peak_bytes;
-    const size_t want = s->pool_peak + s->pool_peak / 4 + ((size_t)64 << 20);
+    const size_t want = s->pool_peak + s->pool_peak / 10 + ((size_t)64 << 20);
     cudaStreamSynchronize(s->st);
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, s->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);  // hand the pool's memory over

@@ -1,6 +1,9 @@
 // optical_flow.cpp -- OpticalFlowBase / OpticalFlowE with the reference's interface and messages
 // (src/optical_flow/optical_flow_base.cpp, optical_flow_e.cpp), implemented on the C ABI.
+#include <dlfcn.h>
+
 #include <cstdio>
+#include <string>
 #include <vector>
 
 #include "flow3d/cuda_utils.h"
@@ -26,6 +29,32 @@ void OpticalFlowBase::ComputeFlow(Data3D&, Data3D&, Data3D&, Data3D&, Data3D&, O
 
 void OpticalFlowBase::Destroy() { initialized_ = false; }
 
+namespace {
+// flow3d_mgpu_compute_host of libflow3d_b200_mgpu.so, which sits next to this library; loaded on first
+// use so that single-GPU programs never need NCCL
+typedef int (*MgpuHostFn)(size_t, size_t, size_t, int, const int*, const float*, const float*, const flow3d_params*, float*,
+                          float*, float*, float*, int);
+MgpuHostFn mgpu_host_fn() {
+  static MgpuHostFn fn = [] {
+    Dl_info info;
+    std::string dir;
+    if (dladdr(reinterpret_cast<void*>(&flow3d_version), &info) && info.dli_fname) {
+      dir = info.dli_fname;
+      const size_t slash = dir.rfind('/');
+      dir = slash == std::string::npos ? std::string() : dir.substr(0, slash + 1);
+    }
+    void* h = dlopen((dir + "libflow3d_b200_mgpu.so").c_str(), RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libflow3d_b200_mgpu.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+      std::printf("Error: cannot load libflow3d_b200_mgpu.so (%s)\n", dlerror());
+      return static_cast<MgpuHostFn>(nullptr);
+    }
+    return reinterpret_cast<MgpuHostFn>(dlsym(h, "flow3d_mgpu_compute_host"));
+  }();
+  return fn;
+}
+}  // namespace
+
 OpticalFlowE::OpticalFlowE() : OpticalFlowBase("Optical Flow Single GPU") {}
 
 OpticalFlowE::~OpticalFlowE() { Destroy(); }
@@ -33,6 +62,17 @@ OpticalFlowE::~OpticalFlowE() { Destroy(); }
 bool OpticalFlowE::Initialize(const DataSize4& data_size) {
   Destroy();
   size_ = data_size;
+  if (devices_.size() > 1) {  // sharded solve: the ranks allocate their slabs on first use
+    if (!mgpu_host_fn()) { last_status_ = FLOW3D_ERR_UNSUPPORTED; return false; }
+    const int n = flow3d_device_count();
+    for (int d : devices_)
+      if (d < 0 || d >= n) { std::printf("Error: no CUDA device %d.\n", d); last_status_ = FLOW3D_ERR_INVALID_ARG; return false; }
+    std::printf("Sharding along z over %zu devices.\n", devices_.size());
+    size_.pitch = flow3d_aligned_ld(data_size.width) * sizeof(float);
+    last_status_ = FLOW3D_OK;
+    initialized_ = true;
+    return true;
+  }
   std::printf("Allocating memory on the device...\n");
   const double mb = flow3d_solver_workspace_bytes(data_size.width, data_size.height, data_size.depth) / (1024.0 * 1024.0);
   std::printf("Needed\t\t:\t%.0fMB\n", mb);
@@ -91,6 +131,20 @@ void OpticalFlowE::ComputeFlow(Data3D& frame_0, Data3D& frame_1, Data3D& flow_u,
     }
   }
   std::printf("\nStarting optical flow computation...\n");
+  if (devices_.size() > 1) {
+    float ms = 0.f;
+    last_status_ = mgpu_host_fn()(size_.width, size_.height, size_.depth, (int)devices_.size(), devices_.data(),
+                                  frame_0.DataPtr(), frame_1.DataPtr(), &p, flow_u.DataPtr(), flow_v.DataPtr(),
+                                  flow_w.DataPtr(), &ms, 1);
+    if (last_status_ != FLOW3D_OK) {
+      std::printf("Error: '%s' failed: %s. %s\n", n, flow3d_status_string(last_status_), flow3d_last_cuda_error());
+      return;
+    }
+    last_ms_[0] = last_ms_[1] = ms;
+    std::printf("Total GPU computation time: % 4.4fs\n", ms / 1000.);
+    return;
+  }
+  flow3d_solver_set_verbose(solver_, silent ? 0 : 1);
   last_status_ = flow3d_solver_compute_host(solver_, frame_0.DataPtr(), frame_1.DataPtr(), &p, flow_u.DataPtr(),
                                             flow_v.DataPtr(), flow_w.DataPtr());
   if (last_status_ != FLOW3D_OK) {
@@ -160,6 +214,8 @@ bool OpticalFlowE::WarpFrame(Data3D& frame_0, Data3D& frame_1, Data3D& flow_u, D
 }
 
 void OpticalFlowE::Destroy() {
+  if (devices_.size() > 1 && initialized_ && mgpu_host_fn())  // release the persistent ranks
+    mgpu_host_fn()(0, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
   if (solver_) {
     flow3d_solver_destroy(solver_);
     solver_ = nullptr;

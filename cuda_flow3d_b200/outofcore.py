@@ -196,7 +196,7 @@ class OutOfCoreFlowSolver:
                  min_planes_per_slab=12, min_voxels_per_slab=1 << 18, cache_static=True):
         self.cache_static = cache_static
         self.device, self.slabs, self.concurrency, self.pinned = int(device), int(slabs), int(concurrency), pinned
-        self.backend_factory = backend_factory  # tests: an OracleBackend per virtual rank (CPU)
+        self.backend_factory = backend_factory  # tests inject a CPU backend per virtual rank
         self.frame_ghost = frame_ghost
         self.min_planes, self.min_voxels = min_planes_per_slab, min_voxels_per_slab
         self.stats = {}

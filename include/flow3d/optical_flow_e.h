@@ -4,6 +4,8 @@
 #ifndef FLOW3D_OPTICAL_FLOW_E_H_
 #define FLOW3D_OPTICAL_FLOW_E_H_
 
+#include <vector>
+
 #include "flow3d/optical_flow_base.h"
 
 struct flow3d_solver;
@@ -28,6 +30,11 @@ class OpticalFlowE : public OpticalFlowBase {
   float last_total_ms() const { return last_ms_[0]; }   // H2D + levels + D2H (the reference's bracket)
   float last_device_ms() const { return last_ms_[1]; }  // levels only
   void SetDevice(int device) { device_ = device; }      // before Initialize(); default 0
+  // Several GPUs of this box (before Initialize()): ComputeFlow then z-shards the volume over them through
+  // libflow3d_b200_mgpu.so (one host thread + one NCCL rank per device, loaded on first use; the result is
+  // bit-identical to the single-GPU one).  Takes the place of the reference's second solver class for
+  // volumes beyond one device, OpticalFlowP (src/optical_flow/optical_flow_p.cpp:58-323).
+  void SetDevices(const std::vector<int>& devices) { devices_ = devices; if (!devices.empty()) device_ = devices[0]; }
   // Convergence diagnostics (flow3d_solver_set_diagnostics): record the Jacobi update norm per level
   // and outer iteration; update_tolerance > 0 stops a level early (results then differ from the
   // reference's fixed iteration count).  Call after Initialize().
@@ -43,6 +50,7 @@ class OpticalFlowE : public OpticalFlowBase {
   flow3d_solver* solver_ = nullptr;
   DataSize4 size_{0, 0, 0, 0};
   int device_ = 0;
+  std::vector<int> devices_;  // > 1 entries: sharded solve
   int last_status_ = 0;
   float last_ms_[2] = {0.f, 0.f};
 };

@@ -306,6 +306,10 @@ int flow3d_solver_last_timing(const flow3d_solver* s, float ms[2]);
 #define FLOW3D_STAGE_COPY 7     /* H2D/D2H or D2D staging copies */
 #define FLOW3D_STAGE_COUNT 8
 int flow3d_solver_set_profiling(flow3d_solver* s, int enable);
+/* enable != 0: every compute call prints the reference's per-level line "Solve level %2d (%4d x%4d x%4d)"
+ * (what OpticalFlowE prints when `silent` is false, src/optical_flow/optical_flow_e.cpp:270-271) as the
+ * level is enqueued */
+int flow3d_solver_set_verbose(flow3d_solver* s, int enable);
 int flow3d_solver_stage_times(flow3d_solver* s, float ms[FLOW3D_STAGE_COUNT],
                               double units[FLOW3D_STAGE_COUNT], uint64_t launches[FLOW3D_STAGE_COUNT]);
 

@@ -97,3 +97,44 @@ def test_cli_diagnostics_and_warped_outputs(gpu, tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     lines = [l for l in r.stdout.splitlines() if l.startswith("level ")]
     assert len(lines) == 4 and all("outer   1" in l for l in lines)
+
+
+@pytest.mark.gpu
+def test_cli_verbose_prints_the_reference_level_lines(gpu, tmp_path):
+    """`silent = false` (optical_flow_e.cpp:270-271): one "Solve level" line per pyramid level"""
+    f0, f1, _ = gpu.ops.synth_pair(40, 36, 32, truth=False)
+    f0.tofile(tmp_path / "a.raw")
+    f1.tofile(tmp_path / "b.raw")
+    cmd = [CLI, "--dims", "40", "36", "32", "--frame0", str(tmp_path / "a.raw"), "--frame1", str(tmp_path / "b.raw"),
+           "--f32", "--param", "warp_levels_count=4", "--param", "warp_scale_factor=0.8", "--param",
+           "outer_iterations_count=2"]
+    quiet = subprocess.run(cmd, capture_output=True, text=True)
+    loud = subprocess.run(cmd + ["--verbose"], capture_output=True, text=True)
+    assert quiet.returncode == 0 and loud.returncode == 0
+    assert "Solve level" not in quiet.stdout
+    lines = [l for l in loud.stdout.splitlines() if l.startswith("Solve level")]
+    assert len(lines) == 4 and lines[-1].startswith("Solve level  0 (  40 x  36 x  32)")
+
+
+@pytest.mark.gpu
+def test_cli_gpus_shards_over_two_devices(gpu, tmp_path):
+    """`flow3d_cli --gpus 2` = OpticalFlowE::SetDevices: C++ host -> libflow3d_b200_mgpu.so (threads + NCCL);
+    the flow must equal the single-GPU flow byte for byte"""
+    if gpu.load().flow3d_device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    f0, f1, _ = gpu.ops.synth_pair(72, 40, 96, truth=False)
+    f0.tofile(tmp_path / "a.raw")
+    f1.tofile(tmp_path / "b.raw")
+    base = [CLI, "--dims", "72", "40", "96", "--frame0", str(tmp_path / "a.raw"), "--frame1", str(tmp_path / "b.raw"),
+            "--f32", "--param", "warp_levels_count=14", "--param", "outer_iterations_count=3"]
+    env = dict(os.environ, FLOW3D_MGPU_MIN_PLANES="8", FLOW3D_MGPU_MIN_VOXELS="1")
+    one = subprocess.run(base + ["--out", str(tmp_path / "one")], capture_output=True, text=True)
+    two = subprocess.run(base + ["--out", str(tmp_path / "two"), "--gpus", "2", "--reps", "2"], capture_output=True,
+                         text=True, env=env)
+    assert one.returncode == 0, one.stdout + one.stderr
+    assert two.returncode == 0, two.stdout + two.stderr
+    assert "Sharding along z over 2 devices." in two.stdout
+    for c in "uvw":
+        a = open(tmp_path / ("one_%s.raw" % c), "rb").read()
+        b = open(tmp_path / ("two_%s.raw" % c), "rb").read()
+        assert a == b

@@ -31,7 +31,8 @@ def _worker(rank, world, port, shape, params, out_dir, slabs=False, overlap=None
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle.oracle import Oracle
-    from cuda_flow3d_b200.dist import OracleBackend, ShardedFlowSolver
+    from cuda_flow3d_b200.dist import ShardedFlowSolver
+    from oracle_backend import OracleBackend
     o = Oracle()
     o.set_num_threads(2)
     f0 = smooth_volume(shape, 21)

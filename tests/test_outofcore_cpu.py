@@ -3,7 +3,8 @@ communicator and the slab bookkeeping, with the test oracle's slab functions as 
 The streamed result must equal the single-solve oracle result bit for bit."""
 import numpy as np
 
-from cuda_flow3d_b200.dist import OracleBackend, ShardedFlowSolver
+from cuda_flow3d_b200.dist import ShardedFlowSolver
+from oracle_backend import OracleBackend
 from cuda_flow3d_b200.outofcore import OutOfCoreFlowSolver
 
 PARAMS = dict(warp_levels_count=4, warp_scale_factor=0.8, outer_iterations_count=2, inner_iterations_count=2,
