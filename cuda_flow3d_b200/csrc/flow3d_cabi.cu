@@ -259,7 +259,11 @@ struct flow3d_solver {
   size_t vol = 0;       // floats per arena volume = ld*H*D
   int device = 0;
   float* arena = nullptr;
-  static constexpr int kVolumes = 19;
+  // 17 full-resolution volumes (the reference keeps 15 containers, optical_flow_e.h:40, but stores neither
+  // the precomputed image derivatives nor a second ping-pong set): blurred frames 2, fx..ft 4, u,v,w 3,
+  // du,dv,dw 3, ping-pong 3 (also resample / median scratch), phi + ksi 2 -- the level frames share the
+  // phi / ksi slots: they are consumed by the warp before the solver writes its first weight.
+  static constexpr int kVolumes = 17;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float last_ms[2] = {0.f, 0.f};
@@ -280,8 +284,8 @@ struct flow3d_solver {
 };
 
 // arena slots
-enum { B_F0 = 0, B_F1, B_F0L, B_F1L, B_FX, B_FY, B_FZ, B_FT, B_U, B_V, B_W, B_DU, B_DV, B_DW, B_TDU,
-       B_TDV, B_TDW, B_PHI, B_KSI };
+enum { B_F0 = 0, B_F1, B_FX, B_FY, B_FZ, B_FT, B_U, B_V, B_W, B_DU, B_DV, B_DW, B_TDU, B_TDV, B_TDW, B_PHI, B_KSI,
+       B_F0L = B_PHI, B_F1L = B_KSI };
 
 // The coarse-to-fine loop (optical_flow_e.cpp:179-473).  in0/in1: device frames with pitch in_ld.
 // On return u/v/w slots (tracked through the swaps) hold the full-resolution flow.

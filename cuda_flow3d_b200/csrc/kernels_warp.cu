@@ -20,7 +20,7 @@ __device__ __forceinline__ float warp_at(const float* __restrict__ f0, const flo
                                          const float* __restrict__ w, const WarpGeom& q, int x, int y,
                                          int z) {
   const Dims& g = q.g;
-  const long long c = (long long)z * g.ps + (long long)y * g.ld + x;
+  const unsigned c = (unsigned)z * (unsigned)g.ps + (unsigned)y * g.ld + x;  // < 2^32 elements per volume
   const float x_f = __fmaf_rn(q.rhx, __ldg(u + c), (float)(unsigned)x);
   const float y_f = __fmaf_rn(q.rhy, __ldg(v + c), (float)(unsigned)y);
   const float z_f = __fmaf_rn(q.rhz, __ldg(w + c), (float)(unsigned)(g.z0g + z));  // global plane
@@ -45,10 +45,9 @@ __device__ __forceinline__ float warp_at(const float* __restrict__ f0, const flo
   const float w10 = __fmul_rn(dx, oy);
   const float w01 = __fmul_rn(ox, dy);
   const float w11 = __fmul_rn(dx, dy);
-  const long long r00 = (long long)z0l * g.ps + (long long)yi * g.ld;
-  const long long r01 = (long long)z0l * g.ps + (long long)y1 * g.ld;
-  const long long r10 = (long long)z1l * g.ps + (long long)yi * g.ld;
-  const long long r11 = (long long)z1l * g.ps + (long long)y1 * g.ld;
+  const unsigned p0 = (unsigned)z0l * (unsigned)g.ps, p1 = (unsigned)z1l * (unsigned)g.ps;
+  const unsigned ra = (unsigned)yi * g.ld, rb = (unsigned)y1 * g.ld;
+  const unsigned r00 = p0 + ra, r01 = p0 + rb, r10 = p1 + ra, r11 = p1 + rb;
   float v0 = __fmul_rn(w10, __ldg(f1 + r00 + x1));
   v0 = __fmaf_rn(w00, __ldg(f1 + r00 + xi), v0);
   v0 = __fmaf_rn(w01, __ldg(f1 + r01 + xi), v0);
@@ -158,17 +157,32 @@ __global__ void __launch_bounds__(WD_TX* WD_TY) warp_derivatives_kernel(
   const ConstDiv fhx = make_const_div(__fmul_rn(hx, 4.f)), fhy = make_const_div(__fmul_rn(hy, 4.f)),
                  fhz = make_const_div(__fmul_rn(hz, 4.f));
   constexpr int CELLS = (WD_TY + 2) * (WD_TX + 2);
+  constexpr int PER = (CELLS + WD_TX * WD_TY - 1) / (WD_TX * WD_TY);  // ring cells per thread (2)
 
-  // fill ring slot `slot` with the warped plane mirror(zz): cell (r,cx) <-> voxel
-  // (mirror(bx-1+cx), mirror(by-1+r)) -- mirrored coordinates reproduce the reference's halo.
+  // Everything that does not change along the march is computed once per thread: the (mirrored) voxel
+  // coordinates of the ring cells this thread fills -- cell (r,cx) <-> voxel (mirror(bx-1+cx), mirror(by-1+r)):
+  // mirrored coordinates reproduce the reference's halo -- and the in-plane offsets of the derivative
+  // stencil.  Offsets are 32-bit (a volume holds < 2^32 elements, checked by the launcher's callers).
+  int cell_x[PER], cell_y[PER], cell_s[PER];
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int i = tid + k * WD_TX * WD_TY;
+    const int r = i / (WD_TX + 2), cx = i - r * (WD_TX + 2);
+    cell_x[k] = mirror_idx(bx - 1 + cx, g.w);
+    cell_y[k] = mirror_idx(by - 1 + r, g.h);
+    cell_s[k] = (i < CELLS) ? r * (WD_TX + 2) + cx : -1;
+  }
+  float* const ring = &sw[0][0][0];
   auto fill = [&](int slot, int zz) {  // zz = local plane index, possibly one beyond a global face
-    const int zs = z_neighbour(g, zz, 0);
-    for (int i = tid; i < CELLS; i += WD_TX * WD_TY) {
-      const int r = i / (WD_TX + 2), cx = i - r * (WD_TX + 2);
-      const int gx = mirror_idx(bx - 1 + cx, g.w), gy = mirror_idx(by - 1 + r, g.h);
-      sw[slot][r][cx] = warp_at(f0, f1, u, v, w, q, gx, gy, zs);
-    }
+    const int zsrc = z_neighbour(g, zz, 0);
+#pragma unroll
+    for (int k = 0; k < PER; ++k)
+      if (cell_s[k] >= 0) ring[slot * CELLS + cell_s[k]] = warp_at(f0, f1, u, v, w, q, cell_x[k], cell_y[k], zsrc);
   };
+  const unsigned ps = (unsigned)g.ps;
+  const unsigned o_c = (unsigned)y * g.ld + x;
+  const unsigned o_xp = (unsigned)y * g.ld + mirror_idx(x + 1, g.w), o_xm = (unsigned)y * g.ld + mirror_idx(x - 1, g.w);
+  const unsigned o_yp = (unsigned)mirror_idx(y + 1, g.h) * g.ld + x, o_ym = (unsigned)mirror_idx(y - 1, g.h) * g.ld + x;
   fill(0, z_begin - 1);
   fill(1, z_begin);
   int sp = 0, sc = 1, sn = 2;
@@ -176,17 +190,13 @@ __global__ void __launch_bounds__(WD_TX* WD_TY) warp_derivatives_kernel(
     fill(sn, z + 1);
     __syncthreads();
     if (valid) {
-      const long long c = (long long)z * g.ps + (long long)y * g.ld + x;
-      const long long ixp = c - x + mirror_idx(x + 1, g.w), ixm = c - x + mirror_idx(x - 1, g.w);
-      const long long rb = (long long)z * g.ps + x;
-      const long long iyp = rb + (long long)mirror_idx(y + 1, g.h) * g.ld;
-      const long long iym = rb + (long long)mirror_idx(y - 1, g.h) * g.ld;
-      const long long cb = (long long)y * g.ld + x;
-      const long long izp = cb + (long long)z_neighbour(g, z, 1) * g.ps;
-      const long long izm = cb + (long long)z_neighbour(g, z, -1) * g.ps;
+      const unsigned pl = (unsigned)z * ps;
+      const unsigned c = pl + o_c;
+      const unsigned izp = (unsigned)z_neighbour(g, z, 1) * ps + o_c;
+      const unsigned izm = (unsigned)z_neighbour(g, z, -1) * ps + o_c;
       const float wc = sw[sc][ty + 1][tx + 1];
-      fx[c] = deriv(__ldg(f0 + ixp), __ldg(f0 + ixm), sw[sc][ty + 1][tx + 2], sw[sc][ty + 1][tx], fhx);
-      fy[c] = deriv(__ldg(f0 + iyp), __ldg(f0 + iym), sw[sc][ty + 2][tx + 1], sw[sc][ty][tx + 1], fhy);
+      fx[c] = deriv(__ldg(f0 + pl + o_xp), __ldg(f0 + pl + o_xm), sw[sc][ty + 1][tx + 2], sw[sc][ty + 1][tx], fhx);
+      fy[c] = deriv(__ldg(f0 + pl + o_yp), __ldg(f0 + pl + o_ym), sw[sc][ty + 2][tx + 1], sw[sc][ty][tx + 1], fhy);
       fz[c] = deriv(__ldg(f0 + izp), __ldg(f0 + izm), sw[sn][ty + 1][tx + 1], sw[sp][ty + 1][tx + 1], fhz);
       ft[c] = __fsub_rn(wc, __ldg(f0 + c));
     }
