@@ -41,6 +41,60 @@ __global__ void __launch_bounds__(256) conv_axis_kernel(const float* __restrict_
   out[c] = sum;
 }
 
+// float4 forms (north-star (a): vectorised, coalesced rows).  y / z passes: a thread owns four consecutive
+// x and reads one float4 per tap.  x pass (compile-time radius R): a thread owns four consecutive outputs
+// and reads its 2R+4-wide window once.  Per output the operations are the scalar kernel's: one fma per tap,
+// j ascending, zero for taps outside the volume.  Columns >= w of a row are padding: whatever is computed
+// there is never interpreted.
+template <int AXIS>
+__global__ void __launch_bounds__(256) conv_axis_vec4_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                             Dims g, ConvTaps taps, int radius, int zs) {
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int z = zs + blockIdx.z;
+  if (x >= g.w || y >= g.h) return;
+  const long long c = (long long)z * g.ps + (long long)y * g.ld + x;
+  const int pos = AXIS == 1 ? y : (g.z0g + z);
+  const int n = AXIS == 1 ? g.h : g.dg;
+  const long long stride = AXIS == 1 ? (long long)g.ld : g.ps;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  for (int j = -radius; j <= radius; ++j) {
+    const int p = pos + j;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p >= 0 && p < n) v = __ldg(reinterpret_cast<const float4*>(in + c + (long long)j * stride));
+    const float t = taps.t[radius - j];
+    s0 = __fmaf_rn(t, v.x, s0);
+    s1 = __fmaf_rn(t, v.y, s1);
+    s2 = __fmaf_rn(t, v.z, s2);
+    s3 = __fmaf_rn(t, v.w, s3);
+  }
+  *reinterpret_cast<float4*>(out + c) = make_float4(s0, s1, s2, s3);
+}
+
+template <int R>
+__global__ void __launch_bounds__(256) conv_x_vec4_kernel(const float* __restrict__ in, float* __restrict__ out, Dims g,
+                                                          ConvTaps taps, int zs) {
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int z = zs + blockIdx.z;
+  if (x >= g.w || y >= g.h) return;
+  const long long row = (long long)z * g.ps + (long long)y * g.ld;
+  float win[2 * R + 4];  // in[x-R .. x+R+3], zero outside [0, w)
+#pragma unroll
+  for (int k = 0; k < 2 * R + 4; ++k) {
+    const int p = x - R + k;
+    win[k] = (p >= 0 && p < g.w) ? __ldg(in + row + p) : 0.f;
+  }
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = -R; j <= R; ++j) {
+    const float t = taps.t[R - j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[i] = __fmaf_rn(t, win[i + j + R], s[i]);
+  }
+  *reinterpret_cast<float4*>(out + row + x) = make_float4(s[0], s[1], s[2], s[3]);
+}
+
 int launch_conv_axis(const float* in, float* out, Dims g, const float* taps_host, int radius,
                      int axis, ZRange zr, cudaStream_t st) {
   if (radius < 0 || radius > F3D_MAX_BLUR_RADIUS) return FLOW3D_ERR_UNSUPPORTED;
@@ -49,6 +103,17 @@ int launch_conv_axis(const float* in, float* out, Dims g, const float* taps_host
   for (int i = 0; i < 2 * radius + 1; ++i) t.t[i] = taps_host[i];
   for (int i = 2 * radius + 1; i < 2 * F3D_MAX_BLUR_RADIUS + 1; ++i) t.t[i] = 0.f;
   dim3 block(32, 8, 1);
+  static const int scalar = [] { const char* e = getenv("FLOW3D_BLUR_SCALAR"); return (e && *e) ? atoi(e) : 0; }();
+  const bool vec_ok = !scalar && (g.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+  if (vec_ok && (axis != 0 || radius == 6 || radius == 3)) {  // sigma = 2 (default) -> 6, sigma = 1 -> 3
+    dim3 grid4((g.w + 127) / 128, (g.h + 7) / 8, zr.end - zr.begin);
+    if (axis == 1) conv_axis_vec4_kernel<1><<<grid4, block, 0, st>>>(in, out, g, t, radius, zr.begin);
+    else if (axis == 2) conv_axis_vec4_kernel<2><<<grid4, block, 0, st>>>(in, out, g, t, radius, zr.begin);
+    else if (radius == 6) conv_x_vec4_kernel<6><<<grid4, block, 0, st>>>(in, out, g, t, zr.begin);
+    else conv_x_vec4_kernel<3><<<grid4, block, 0, st>>>(in, out, g, t, zr.begin);
+    count_launch();
+    return check_launch("conv_axis_vec4_kernel");
+  }
   dim3 grid((g.w + 31) / 32, (g.h + 7) / 8, zr.end - zr.begin);
   if (axis == 0) conv_axis_kernel<0><<<grid, block, 0, st>>>(in, out, g, t, radius, zr.begin);
   else if (axis == 1) conv_axis_kernel<1><<<grid, block, 0, st>>>(in, out, g, t, radius, zr.begin);
