@@ -1119,7 +1119,7 @@ int flow3d_solver_diagnostics(flow3d_solver* s, size_t* n_levels, size_t* outer_
 }
 
 int flow3d_selftest_fast_div(uint64_t n_pairs, uint64_t seed, int mode, uint64_t out[3]) {
-  if (!out || n_pairs == 0 || (mode != 0 && mode != 1)) return FLOW3D_ERR_INVALID_ARG;
+  if (!out || n_pairs == 0 || mode < 0 || mode > 3) return FLOW3D_ERR_INVALID_ARG;
   if (flow3d_device_count() <= 0) return FLOW3D_ERR_NO_DEVICE;
   unsigned long long r[3] = {0, 0, 0};
   F3D_TRY(launch_fast_div_selftest(n_pairs, seed, mode, r));

@@ -125,6 +125,16 @@ __global__ void __launch_bounds__(256) fast_div_selftest_kernel(unsigned long lo
   unsigned long long bad = 0, rejected = 0, tested = 0;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (unsigned long long)gridDim.x * blockDim.x) {
+    if (mode >= 2) {  // unary: every float bit pattern i (mode 2: sqrt_fast, mode 3: rcp_fast)
+      const float x = __uint_as_float((unsigned)i);
+      bool ok = true;
+      const float q = mode == 2 ? sqrt_fast(x, ok) : rcp_fast(x, ok);
+      const float ref = mode == 2 ? __fsqrt_rn(x) : __frcp_rn(x);
+      ++tested;
+      if (!ok) ++rejected;
+      else if (__float_as_uint(q) != __float_as_uint(ref)) ++bad;
+      continue;
+    }
     float a, b;
     if (mode == 0) {
       a = make_operand(mix64(seed + 2 * i));

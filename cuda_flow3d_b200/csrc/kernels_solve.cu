@@ -329,8 +329,15 @@ __device__ __forceinline__ void sweep_plane(const SweepArgs& a, const Dims& g, c
       const float r4 = __fmaf_rn(gt, gt, __fmaf_rn(J34, dw, __fmaf_rn(J14, du, __fmul_rn(J24, dv))));
       float sv = __fadd_rn(__fmaf_rn(dw, r3, __fmaf_rn(du, r1, __fmul_rn(dv, r2))), r4);
       sv = __fmul_rn(sv, (sv > 0.f) ? 1.f : 0.f);
-      const float sq2 = __fsqrt_rn(__fmaf_rn(a.eps_d, a.eps_d, sv));
-      ks.v[i] = __frcp_rn(__fadd_rn(sq2, sq2));
+      const float arg = __fmaf_rn(a.eps_d, a.eps_d, sv);
+      bool ok2 = true;
+      float sq2 = sqrt_fast(arg, ok2);
+      float kk = rcp_fast(__fadd_rn(sq2, sq2), ok2);
+      if (!ok2) {
+        sq2 = __fsqrt_rn(arg);
+        kk = __frcp_rn(__fadd_rn(sq2, sq2));
+      }
+      ks.v[i] = kk;
     }
     const float k = ks.v[i];
     const float ndu = __fmaf_rn(-J13, C.dw.v[i], __fmaf_rn(-J12, C.dv.v[i], -J14));
@@ -960,8 +967,16 @@ __device__ __forceinline__ void phi_ksi_body(const PhiKsiArgs& a, const LaneMap&
         for (int k = 0; k < 9; ++k) q[k] = __fdiv_rn(nm[k], (k % 3 == 0) ? thx.c : (k % 3 == 1) ? thy.c : thz.c);
         acc = sum_sq(q);
       }
-      const float sq = __fsqrt_rn(acc);
-      ophi.v[i] = __frcp_rn(__fadd_rn(sq, sq));
+      {  // 1 / (2 sqrt(acc)): branch-free fast paths (common.cuh), IEEE intrinsics outside their range
+        bool ok = true;
+        float sq = sqrt_fast(acc, ok);
+        float ph = rcp_fast(__fadd_rn(sq, sq), ok);
+        if (!ok) {
+          sq = __fsqrt_rn(acc);
+          ph = __frcp_rn(__fadd_rn(sq, sq));
+        }
+        ophi.v[i] = ph;
+      }
       if constexpr (WITH_KSI) {
         const float gx = fx.v[i], gy = fy.v[i], gz = fz.v[i], gt = ft.v[i];
         const float J11 = __fmul_rn(gx, gx), J22 = __fmul_rn(gy, gy), J33 = __fmul_rn(gz, gz);
@@ -975,8 +990,15 @@ __device__ __forceinline__ void phi_ksi_body(const PhiKsiArgs& a, const LaneMap&
         const float r4 = __fmaf_rn(gt, gt, __fmaf_rn(J34, dw, __fmaf_rn(J14, du, __fmul_rn(J24, dv))));
         float sv = __fadd_rn(__fmaf_rn(dw, r3, __fmaf_rn(du, r1, __fmul_rn(dv, r2))), r4);
         sv = __fmul_rn(sv, (sv > 0.f) ? 1.f : 0.f);
-        const float sq2 = __fsqrt_rn(__fmaf_rn(a.eps_d, a.eps_d, sv));
-        oksi.v[i] = __frcp_rn(__fadd_rn(sq2, sq2));
+        const float arg = __fmaf_rn(a.eps_d, a.eps_d, sv);
+        bool ok2 = true;
+        float sq2 = sqrt_fast(arg, ok2);
+        float ks = rcp_fast(__fadd_rn(sq2, sq2), ok2);
+        if (!ok2) {
+          sq2 = __fsqrt_rn(arg);
+          ks = __frcp_rn(__fadd_rn(sq2, sq2));
+        }
+        oksi.v[i] = ks;
       }
     }
     if (active) {

@@ -447,8 +447,14 @@ __device__ __forceinline__ void sweep_tma_run(const TmaMaps& maps, const SweepAr
           const float r4 = __fmaf_rn(gt, gt, __fmaf_rn(J34, dwc, __fmaf_rn(J14, duc, __fmul_rn(J24, dvc))));
           float sv = __fadd_rn(__fmaf_rn(dwc, r3, __fmaf_rn(duc, r1, __fmul_rn(dvc, r2))), r4);
           sv = __fmul_rn(sv, (sv > 0.f) ? 1.f : 0.f);
-          const float sq2 = __fsqrt_rn(__fmaf_rn(a.eps_d, a.eps_d, sv));
-          k = __frcp_rn(__fadd_rn(sq2, sq2));
+          const float arg = __fmaf_rn(a.eps_d, a.eps_d, sv);
+          bool ok2 = true;
+          float sq2 = sqrt_fast(arg, ok2);
+          k = rcp_fast(__fadd_rn(sq2, sq2), ok2);
+          if (!ok2) {
+            sq2 = __fsqrt_rn(arg);
+            k = __frcp_rn(__fadd_rn(sq2, sq2));
+          }
         }
         // solve_3d.cu:492-502; numerators as the reference's SASS evaluates them
         const float ndu = __fmaf_rn(-J13, dwc, __fmaf_rn(-J12, dvc, -J14));

@@ -343,7 +343,9 @@ int flow3d_solver_diagnostics(flow3d_solver* s, size_t* n_levels, size_t* outer_
 /* ---- self-test ------------------------------------------------------------------------------------
  * The sweep kernels divide with the branch-free fast path of div.rn.f32 (csrc/common.cuh: div_fast) and
  * fall back to the IEEE division for operands outside [2^-60, 2^60].  This runs n_pairs divisions on the
- * device both ways: mode 0 = random operands, mode 1 = every divisor mantissa (n_pairs = k * 2^23).
+ * device both ways: mode 0 = random operands, mode 1 = every divisor mantissa (n_pairs = k * 2^23).  Modes 2 / 3
+ * check the branch-free sqrt / reciprocal of the robust weights (sqrt_fast, rcp_fast) against __fsqrt_rn / __frcp_rn on
+ * the float whose bit pattern is i, for i < n_pairs (2^32 = every float).
  * out[0] = quotients that differ from IEEE division (must be 0), out[1] = pairs sent to the fallback,
  * out[2] = pairs tested.  Synchronous. */
 int flow3d_selftest_fast_div(uint64_t n_pairs, uint64_t seed, int mode, uint64_t out[3]);

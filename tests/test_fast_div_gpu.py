@@ -25,3 +25,12 @@ def test_fast_div_every_divisor_mantissa(gpu, lib):
     for seed in (1, 2, 3):
         bad, rejected, tested = _run(lib, 64 << 23, seed, 1)
         assert tested == 64 << 23 and bad == 0 and rejected == 0
+
+
+def test_fast_sqrt_and_rcp_every_float(gpu, lib):
+    """sqrt_fast / rcp_fast (the robust weights 1 / (2 sqrt(s))) against __fsqrt_rn / __frcp_rn on every float
+    bit pattern: no accepted argument may differ; the accepted set must cover the normal range they are used on"""
+    for mode in (2, 3):
+        bad, rejected, tested = _run(lib, 1 << 32, 0, mode)
+        assert tested == 1 << 32 and bad == 0
+        assert rejected < (1 << 32) * 0.6  # sqrt rejects negatives, tiny values, Inf/NaN; rcp rejects few
