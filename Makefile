@@ -19,7 +19,7 @@ HOST_OBJS := $(HOST_SRCS:.cpp=.o)
 
 all: $(LIB) $(MGPU_LIB) oracle apps
 
-$(CSRC)/kernels_median.o: $(CSRC)/median_net_27.inc $(CSRC)/median_net_125.inc $(CSRC)/median5_sort25.inc
+$(CSRC)/kernels_median.o: $(CSRC)/median_net_27.inc $(CSRC)/median5_sort25.inc
 
 $(CSRC)/median5_sort25.inc: scripts/gen_median5_pair.py
 	python3 scripts/gen_median5_pair.py $(CSRC)

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <string>
 #include <vector>
 
@@ -112,15 +113,30 @@ int main(int argc, char** argv) {
   if (!solver.Initialize(size)) return 1;
   if (diagnostics && !solver.SetDiagnostics(true, tolerance)) return 1;
   Data3D u(W, H, D), v(W, H, D), w(W, H, D);
-  Data3D a, b;
+  Data3D a, b, ahead;
+  // pair mode: the file of the NEXT pair's second frame is read by a helper thread while the current pair is
+  // being solved (the reference re-reads both frames and re-initialises the solver per pair, main.cpp:132-182)
+  std::future<bool> ahead_ready;
+  std::string ahead_path;
 
+  std::string next_path;  // set by the pair loop: file to read ahead during this solve ("" = none)
   auto solve_pair = [&](const std::string& p0, const std::string& p1, const std::string& prefix) -> int {
     if (a.Width() == 0 || !pattern.empty()) {
       // in pair mode frame i+1 of the previous pair becomes frame i of this one (no re-read)
       if (!pattern.empty() && b.Width() == W) a.Swap(b);
       else if (!read_frame(a, p0, f32, W, H, D)) return 2;
     }
-    if (!read_frame(b, p1, f32, W, H, D)) return 2;
+    if (ahead_ready.valid() && ahead_path == p1) {  // read ahead during the previous solve
+      if (!ahead_ready.get()) return 2;
+      b.Swap(ahead);
+    } else {
+      if (ahead_ready.valid()) ahead_ready.get();
+      if (!read_frame(b, p1, f32, W, H, D)) return 2;
+    }
+    if (!next_path.empty()) {
+      ahead_path = next_path;
+      ahead_ready = std::async(std::launch::async, [&, path = next_path] { return read_frame(ahead, path, f32, W, H, D); });
+    }
     for (int r = 0; r < reps; ++r) {
       solver.ComputeFlow(a, b, u, v, w, params);
       if (solver.last_status() != FLOW3D_OK) return 1;
@@ -152,8 +168,15 @@ int main(int argc, char** argv) {
     for (long i = first; i < last && rc == 0; ++i) {
       std::snprintf(n0, sizeof(n0), pattern.c_str(), (int)i);
       std::snprintf(n1, sizeof(n1), pattern.c_str(), (int)(i + 1));
+      next_path.clear();
+      if (i + 2 <= last) {
+        char n2[4096];
+        std::snprintf(n2, sizeof(n2), pattern.c_str(), (int)(i + 2));
+        next_path = n2;
+      }
       rc = solve_pair(n0, n1, out.empty() ? std::string() : out + "_" + std::to_string(i));
     }
+    if (ahead_ready.valid()) ahead_ready.get();
   }
   solver.Destroy();
   return rc;

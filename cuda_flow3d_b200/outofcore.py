@@ -151,8 +151,10 @@ class HostStreamedBackend:
                 if self.cache_static:
                     self._static_key, self._static_dev = key, (dt, du, dv, dw)
             dc = [self._up(t) for t in d_cur]
-            da = [torch.empty_like(t) for t in dc]
-            dphi, dksi = torch.empty_like(dc[0]), torch.empty_like(dc[0])
+            # zero-initialised: with an odd sweep count the result lives in the scratch set, whose outermost
+            # ghost planes no sweep writes -- they go back to the host and must not carry garbage / NaN
+            da = [torch.zeros_like(t) for t in dc]
+            dphi, dksi = torch.zeros_like(dc[0]), torch.zeros_like(dc[0])
             rc, _ = self.inner.outer_iteration(dt, du, dv, dw, dc, da, dphi, dksi, h, inner, alpha, eps_s, eps_d,
                                                lo1, hi1)
             for d, hst in zip(rc, d_cur):

@@ -138,3 +138,28 @@ def test_cli_gpus_shards_over_two_devices(gpu, tmp_path):
         a = open(tmp_path / ("one_%s.raw" % c), "rb").read()
         b = open(tmp_path / ("two_%s.raw" % c), "rb").read()
         assert a == b
+
+
+@pytest.mark.gpu
+def test_cli_pairs_batch_mode_matches_single_pairs(gpu, tmp_path):
+    """--pairs PATTERN FIRST LAST: consecutive pairs with the solver kept alive, frame i+1 reused as frame i and
+    the next file read during the current solve; every pair's flow must equal the flow of that pair run alone"""
+    frames = []
+    rng = np.random.default_rng(5)
+    base = (rng.random((16, 24, 32)) * 200).astype(np.float32)
+    for i in range(4):
+        f = np.roll(base, i, axis=2) + np.float32(i)
+        f.tofile(tmp_path / ("fr_%04d.raw" % i))
+        frames.append(f)
+    common = ["--dims", "32", "24", "16", "--f32", "--param", "warp_levels_count=3", "--param", "outer_iterations_count=2"]
+    r = subprocess.run([CLI, "--pairs", str(tmp_path / "fr_%04d.raw"), "0", "3", "--out", str(tmp_path / "b")] + common,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("FLOW3D_SOLVE") == 3
+    for i in range(3):
+        s = subprocess.run([CLI, "--frame0", str(tmp_path / ("fr_%04d.raw" % i)), "--frame1",
+                            str(tmp_path / ("fr_%04d.raw" % (i + 1))), "--out", str(tmp_path / ("s%d" % i))] + common,
+                           capture_output=True, text=True)
+        assert s.returncode == 0, s.stdout + s.stderr
+        for c in "uvw":
+            assert open(tmp_path / ("b_%d_%s.raw" % (i, c)), "rb").read() == open(tmp_path / ("s%d_%s.raw" % (i, c)), "rb").read()
