@@ -17,9 +17,16 @@
 //                                IN PLACE (one rounded add per voxel, shared by its six consumers, exactly
 //                                the value the reference forms per neighbour: solve_3d.cu:470-490) and
 //                                copies dv,dw (the centre-only raw increments) to a compact ring D;
-//                    one __syncthreads.
+//                    one CTA-wide named barrier (producer warp included).
 // The z-1 and centre values of S and phi of a thread's own column are carried in registers, which is what
-// lets four A slots cover a prefetch distance of three planes.
+// lets four A slots cover a prefetch distance of three planes.  Rings B and C are refilled one step before
+// their first use (shared memory is spent on ring A: 112 KB per CTA, two CTAs per SM), so the arithmetic
+// threads prefetch their own 16 B of those fields into L2 three planes ahead.
+//
+// Status: bit-identical to the register-marching kernel of kernels_solve.cu on every test,
+// 1.42 ms against its 1.34 ms per 512^3 sweep on a B200 -- both end up bound by the ~185 instructions per
+// voxel-sweep at two warps per scheduler, not by memory.  It is therefore not in the default tuning
+// candidates (FLOW3D_TUNE_TMA=1 adds it); flow3d_sweep_shape / FLOW3D_SWEEP_VARIANT select it explicitly.
 //
 // Arithmetic: the same explicit round-to-nearest operation sequence as kernels_solve.cu (bit-identical to
 // the reference's compiled kernels); mirror (reflect-101) neighbours are substituted exactly where the
