@@ -583,7 +583,7 @@ static std::string tune_cache_path(int dev) {
   const std::string dir = std::string(home) + "/.cache/flow3d_b200";
   const std::string cmd = "mkdir -p '" + dir + "' 2>/dev/null";
   if (std::system(cmd.c_str()) != 0) return std::string();
-  return dir + "/tune_v2_" + name + "_" + std::to_string(prop.multiProcessorCount) + ".txt";
+  return dir + "/tune_v3_" + name + "_" + std::to_string(prop.multiProcessorCount) + ".txt";
 }
 // g_tune_mu held
 static void tune_load_locked(int dev) {
