@@ -557,8 +557,12 @@ struct TuneKey {
   }
 };
 enum { TK_SWEEP = 0, TK_PHI_KSI = 1, TK_SWEEP_KSI = 2, TK_PHI = 3 };
+struct TuneEntry {
+  TuneCfg cfg;
+  bool full;  // false: from a quick pass (implicit first-use tuning); a full pass replaces it; never persisted
+};
 static std::mutex g_tune_mu;
-static std::map<TuneKey, TuneCfg> g_tune;
+static std::map<TuneKey, TuneEntry> g_tune;
 static unsigned long long g_tune_loaded = 0;  // bit per device: persisted table read
 
 static bool autotune_enabled() {
@@ -599,13 +603,14 @@ static void tune_load_locked(int dev) {
   while (std::fscanf(f, "%d %d %d %d %d %d %d %d", &k.kernel, &k.w, &k.h, &k.ld, &k.nzq, &c.vec, &c.nchunks,
                      &c.variant) == 8) {
     if ((c.vec == 1 || c.vec == 2 || c.vec == 4) && c.nchunks >= 0 && c.variant >= 0 && c.variant < SWEEP_VARIANT_COUNT)
-      g_tune.emplace(k, c);
+      g_tune.emplace(k, TuneEntry{c, true});
   }
   std::fclose(f);
 }
-static void tune_store(const TuneKey& k, const TuneCfg& c) {
+static void tune_store(const TuneKey& k, const TuneCfg& c, bool full) {
   std::lock_guard<std::mutex> lk(g_tune_mu);
-  g_tune[k] = c;
+  g_tune[k] = TuneEntry{c, full};
+  if (!full) return;
   const std::string path = tune_cache_path(k.dev);
   if (path.empty()) return;
   if (FILE* f = std::fopen(path.c_str(), "a")) {
@@ -613,13 +618,14 @@ static void tune_store(const TuneKey& k, const TuneCfg& c) {
     std::fclose(f);
   }
 }
-static bool tune_lookup(const TuneKey& k, TuneCfg* c) {
+// need_full: an entry from a quick pass does not count
+static bool tune_lookup(const TuneKey& k, TuneCfg* c, bool need_full = false) {
   if (!autotune_enabled()) return false;
   std::lock_guard<std::mutex> lk(g_tune_mu);
   tune_load_locked(k.dev);
   auto it = g_tune.find(k);
-  if (it == g_tune.end()) return false;
-  *c = it->second;
+  if (it == g_tune.end() || (need_full && !it->second.full)) return false;
+  *c = it->second.cfg;
   return true;
 }
 // whole-level launches are keyed by their depth; slab launches (ranges that shrink sweep by sweep inside
@@ -636,7 +642,7 @@ static inline int chunk_len(int nz, int nchunks) {
 }
 // candidate chunk counts: chunk lengths around the static heuristic's choice, plus short chunks (2..8
 // planes) that shorten the dependent z march of small, latency-bound levels
-static void chunk_candidates(int nz, long long per_plane, std::vector<int>& out) {
+static void chunk_candidates(int nz, long long per_plane, std::vector<int>& out, bool quick = false) {
   const long long want = (long long)sm_count() * 16;
   long long n0 = (want + per_plane - 1) / per_plane;
   if (n0 < 1) n0 = 1;
@@ -645,10 +651,12 @@ static void chunk_candidates(int nz, long long per_plane, std::vector<int>& out)
   int lens[16];
   int nl = 0;
   const double f[] = {4.0, 2.0, 1.333, 1.0, 0.667, 0.5};
-  for (double k : f) lens[nl++] = (int)(len0 * k + 0.5);
+  const double fq[] = {2.0, 1.0, 0.5};
+  if (quick) for (double k : fq) lens[nl++] = (int)(len0 * k + 0.5);
+  else for (double k : f) lens[nl++] = (int)(len0 * k + 0.5);
   const int small_lens[] = {2, 4, 8};
   for (int l : small_lens)
-    if (l < len0) lens[nl++] = l;
+    if (l < len0 && (!quick || l == 4)) lens[nl++] = l;
   out.clear();
   for (int i = 0; i < nl; ++i) {
     int len = lens[i] < 2 ? 2 : lens[i];
@@ -664,7 +672,7 @@ static void chunk_candidates(int nz, long long per_plane, std::vector<int>& out)
 // SYNCHRONOUS; the launches are excluded from flow3d_launch_count.
 template <class Launch>
 static int tune_pick(const std::vector<TuneCfg>& cands, Launch&& launch, cudaStream_t st, TuneCfg* best,
-                     const char* what = "") {
+                     const char* what = "", int rounds = 2) {
   if (cands.empty()) return FLOW3D_OK;
   cudaEvent_t e0, e1;
   if (cudaEventCreate(&e0) != cudaSuccess) return FLOW3D_ERR_CUDA;
@@ -687,7 +695,7 @@ static int tune_pick(const std::vector<TuneCfg>& cands, Launch&& launch, cudaStr
   int reps = warm_ms > 0.f ? (int)(2.0f / warm_ms + 0.999f) : 4;
   reps = reps < 4 ? 4 : (reps > 40 ? 40 : reps);
   std::vector<float> t(cands.size(), -1.f);
-  for (int round = 0; round < 2 && rc == FLOW3D_OK; ++round) {
+  for (int round = 0; round < rounds && rc == FLOW3D_OK; ++round) {
     for (size_t i = 0; i < cands.size() && rc == FLOW3D_OK; ++i) {
       float ms = 0.f;
       const int k = timed(cands[i], reps, &ms);
@@ -764,13 +772,14 @@ static TuneCfg static_sweep_cfg(const Dims& g, ZRange zr) {
   return cfg;
 }
 
-static void sweep_candidates(const Dims& g, ZRange zr, std::vector<TuneCfg>& cands) {
+static void sweep_candidates(const Dims& g, ZRange zr, std::vector<TuneCfg>& cands, bool quick = false) {
   const int nz = zr.end - zr.begin;
   const int v0 = pick_vec(g);
   int vecs[2] = {v0, 0};
   if (v0 == 4) vecs[1] = 2;
   else if (v0 == 2 && g.w >= 128) vecs[1] = 4;
   else if (v0 == 2) vecs[1] = 1;  // narrow levels: more, thinner warps
+  if (quick) vecs[1] = 0;
   std::vector<int> chunks;
   for (int vi = 0; vi < 2; ++vi) {
     const int vec = vecs[vi];
@@ -778,14 +787,14 @@ static void sweep_candidates(const Dims& g, ZRange zr, std::vector<TuneCfg>& can
     const int lpr = pick_lpr(g.w, vec);
     const long long per_plane =
         (long long)((g.w + lpr * vec - 1) / (lpr * vec)) * ((g.h + 4 * (32 / lpr) - 1) / (4 * (32 / lpr)));
-    chunk_candidates(nz, per_plane, chunks);
+    chunk_candidates(nz, per_plane, chunks, quick);
     for (int c : chunks) cands.push_back(TuneCfg{vec, c, SWEEP_VARIANT_REG});
   }
   // The TMA-staged tile kernel (kernels_sweep_tma.cu) is a candidate only on request: measured on B200 it
   // trails the register kernel on every level (512^3: 1.42 ms vs 1.34 ms), so timing it
   // only lengthens the tuning pass.  FLOW3D_TUNE_TMA=1 adds it.
   static const int tune_tma = env_int("FLOW3D_TUNE_TMA", 0);
-  for (int variant = 1; tune_tma && variant < SWEEP_VARIANT_COUNT; ++variant) {
+  for (int variant = 1; tune_tma && !quick && variant < SWEEP_VARIANT_COUNT; ++variant) {
     if (!sweep_variant_is_tma(variant) || !sweep_tma_usable(g, variant) || g.w < 128 || g.h < 32 || nz < 32) continue;
     const int lens[] = {64, 128};
     int seen[8], ns = 0;
@@ -1081,15 +1090,19 @@ int launch_phi_ksi(const float* fx, const float* fy, const float* fz, const floa
 // size; they are filled with a finite positive pattern (0x3f3f3f3f = 0.747) so that no candidate runs
 // through denormal / NaN slow paths.
 // ------------------------------------------------------------------------------------------------
-int tune_level_kernels(Dims g, ZRange zr, float* const bufs[16], float hx, float hy, float hz, cudaStream_t st) {
+// quick: the implicit first-use pass of flow3d_solver_compute_host -- the static vector width, four chunk
+// lengths, one timing round (~5x cheaper); its entries stay in memory and are replaced by a full pass.
+int tune_level_kernels(Dims g, ZRange zr, float* const bufs[16], float hx, float hy, float hz, cudaStream_t st,
+                       bool quick) {
   if (!autotune_enabled()) return FLOW3D_OK;
   const int nz = zr.end - zr.begin;
   if (nz < 4) return FLOW3D_OK;
   const TuneKey k_sweep = tune_key(TK_SWEEP, g, zr), k_ksi = tune_key(TK_SWEEP_KSI, g, zr),
                 k_phi = tune_key(TK_PHI, g, zr);
   TuneCfg tmp;
-  const bool have_sweep = tune_lookup(k_sweep, &tmp), have_ksi = tune_lookup(k_ksi, &tmp),
-             have_phi = tune_lookup(k_phi, &tmp);
+  const bool have_sweep = tune_lookup(k_sweep, &tmp, !quick), have_ksi = tune_lookup(k_ksi, &tmp, !quick),
+             have_phi = tune_lookup(k_phi, &tmp, !quick);
+  const int rounds = quick ? 1 : 2;
   if (have_sweep && have_ksi && have_phi) return FLOW3D_OK;
   const size_t bytes = (size_t)g.ps * g.d * sizeof(float);
   for (int i = 0; i < 16; ++i)
@@ -1106,26 +1119,26 @@ int tune_level_kernels(Dims g, ZRange zr, float* const bufs[16], float hx, float
     return (const char*)lbl;
   };
   if (!have_sweep) {
-    sweep_candidates(g, zr, cands);
+    sweep_candidates(g, zr, cands, quick);
     best = static_sweep_cfg(g, zr);
-    F3D_TRY_RC(tune_pick(cands, [&](TuneCfg c) { return launch_sweep_cfg(a, g, zr, c, st); }, st, &best, label("sweep")));
-    tune_store(k_sweep, best);
+    F3D_TRY_RC(tune_pick(cands, [&](TuneCfg c) { return launch_sweep_cfg(a, g, zr, c, st); }, st, &best, label("sweep"), rounds));
+    tune_store(k_sweep, best, !quick);
   }
   if (!have_ksi) {
     SweepArgs ak = a;
     ak.oksi = bufs[15];
     cands.clear();
-    sweep_candidates(g, zr, cands);
+    sweep_candidates(g, zr, cands, quick);
     best = static_sweep_cfg(g, zr);
-    F3D_TRY_RC(tune_pick(cands, [&](TuneCfg c) { return launch_sweep_cfg(ak, g, zr, c, st); }, st, &best, label("sweep+ksi")));
-    tune_store(k_ksi, best);
+    F3D_TRY_RC(tune_pick(cands, [&](TuneCfg c) { return launch_sweep_cfg(ak, g, zr, c, st); }, st, &best, label("sweep+ksi"), rounds));
+    tune_store(k_ksi, best, !quick);
   }
   if (!have_phi) {
     PhiKsiArgs pa{bufs[0], bufs[1], bufs[2], bufs[3], bufs[4], bufs[5], bufs[6], bufs[7], bufs[8], bufs[9], bufs[10],
                   nullptr, g, hx, hy, hz, eps, eps};
     cands.clear();
     const int v0 = static_phi_vec(g);
-    int vecs[2] = {v0, (v0 == 2 && g.w >= 128) ? 4 : 0};
+    int vecs[2] = {v0, (v0 == 2 && g.w >= 128 && !quick) ? 4 : 0};
     std::vector<int> chunks;
     for (int vi = 0; vi < 2; ++vi) {
       const int vc = vecs[vi];
@@ -1133,12 +1146,12 @@ int tune_level_kernels(Dims g, ZRange zr, float* const bufs[16], float hx, float
       const int lpr = pick_lpr(g.w, vc);
       const long long per_plane =
           (long long)((g.w + lpr * vc - 1) / (lpr * vc)) * ((g.h + 4 * (32 / lpr) - 1) / (4 * (32 / lpr)));
-      chunk_candidates(nz, per_plane, chunks);
+      chunk_candidates(nz, per_plane, chunks, quick);
       for (int c : chunks) cands.push_back(TuneCfg{vc, c, 0});
     }
     best = TuneCfg{v0, 0, 0};
-    F3D_TRY_RC(tune_pick(cands, [&](TuneCfg c) { return launch_phi_ksi_cfg(pa, g, zr, c, st); }, st, &best, label("phi")));
-    tune_store(k_phi, best);
+    F3D_TRY_RC(tune_pick(cands, [&](TuneCfg c) { return launch_phi_ksi_cfg(pa, g, zr, c, st); }, st, &best, label("phi"), rounds));
+    tune_store(k_phi, best, !quick);
   }
   return FLOW3D_OK;
 }

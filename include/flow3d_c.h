@@ -279,7 +279,8 @@ int flow3d_solver_compute_device(flow3d_solver* s, const float* frame_0, const f
  * missing entry = static heuristic), so flow3d_solver_compute_device and the stage calls stay
  * asynchronous and capturable.  These calls fill the table; they time candidates with CUDA events and
  * are SYNCHRONOUS.  The table is persisted in $FLOW3D_TUNE_CACHE (default ~/.cache/flow3d_b200/, "off"
- * disables); FLOW3D_AUTOTUNE=0 ignores it.  flow3d_solver_compute_host tunes on first use.
+ * disables); FLOW3D_AUTOTUNE=0 ignores it.  flow3d_solver_compute_host runs a quick pass on first use (static
+ * vector width, four chunk lengths, one timing round; kept in memory only); flow3d_solver_tune runs the full pass.
  * flow3d_tune_kernels: scratch = 16 volumes of the slab's size (contents destroyed). */
 int flow3d_solver_tune(flow3d_solver* s, const flow3d_params* params);
 int flow3d_tune_kernels(const size_t dims[3], size_t ld, const flow3d_zslab* slab, const float h[3],
