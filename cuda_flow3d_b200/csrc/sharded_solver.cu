@@ -391,7 +391,8 @@ struct Frames {
       *out = o;
       return FLOW3D_OK;
     }
-    if (level == 0) return FLOW3D_ERR_INVALID_ARG;  // frame ghost depth too small for the finest level
+    // (level 0 included: a finest level too thin to shard is computed by every rank, each of which then needs
+    // every plane -- the all-gather's "resample" from D to D planes is the identity, bit for bit)
     if (gathered_level[which] != level) {
       s->release(gathered[which]);
       gathered[which] = nullptr;
@@ -779,6 +780,105 @@ int flow3d_sharded_output_planes(const flow3d_sharded* s, const flow3d_params* p
   return FLOW3D_OK;
 }
 
+// Host-only dry run of the partition arithmetic of a solve (no device, no communicator): for every level and
+// rank it checks what solve() relies on -- the prolongation's source planes lie inside the previous level's
+// valid planes of the same rank, neighbours agree on the size of every ghost exchange, and every all-gather
+// piece of a level frame comes from the rank's own frame slab.  flow3d_sharded_compute runs it first, so that a
+// geometry it cannot handle fails on EVERY rank before any rank has entered a collective.
+int flow3d_sharded_plan_check(size_t width, size_t height, size_t depth, int world, const flow3d_params* p,
+                              size_t min_planes_per_rank, size_t min_voxels_per_rank, size_t frame_ghost,
+                              int* bad_level, int* bad_rank) {
+  if (!p || world < 1 || width < 2 || height < 2 || depth < 2) return FLOW3D_ERR_INVALID_ARG;
+  flow3d_sharded t;
+  t.W = width; t.H = height; t.D = depth; t.world = world;
+  t.min_planes = std::max<size_t>(min_planes_per_rank, 1);
+  t.min_voxels = std::max<size_t>(min_voxels_per_rank, 1);
+  const size_t Hg = p->inner_iterations_count + 1;
+  size_t r = p->median_radius;
+  if (r % 2 == 0 && r > 1) r -= 1;
+  const size_t r2 = r / 2;
+  auto fail = [&](int level, int rank) {
+    if (bad_level) *bad_level = level;
+    if (bad_rank) *bad_rank = rank;
+    return FLOW3D_ERR_INVALID_ARG;
+  };
+  const std::vector<Level> sched = schedule(&t, p);
+  std::vector<size_t> pv_lo(world, 0), pv_hi(world, 0);
+  size_t pd = 0;
+  bool have_prev = false;
+  for (const Level& L : sched) {
+    const size_t d = L.dims[2];
+    const bool sharded = is_sharded(&t, L.dims, Hg);
+    std::vector<size_t> a(world), b(world), A(world), B(world);
+    for (int k = 0; k < world; ++k) level_ranges(&t, L.dims, Hg, k, sharded, &a[k], &b[k], &A[k], &B[k]);
+    for (int k = 0; k < world; ++k) {
+      if (b[k] <= a[k] || A[k] > a[k] || B[k] < b[k] || B[k] > d) return fail(L.level, k);
+      if (sharded) {
+        if (k + 1 < world && (b[k] != a[k + 1] || std::min(Hg, b[k] - a[k]) != a[k + 1] - A[k + 1] ||
+                              std::min(Hg, b[k + 1] - a[k + 1]) != B[k] - b[k]))
+          return fail(L.level, k);  // what one side sends != the ghost planes the other side receives into
+        if (k == 0 && a[k] != 0) return fail(L.level, k);
+        if (k == world - 1 && b[k] != d) return fail(L.level, k);
+      }
+      if (have_prev) {
+        size_t s_lo, s_hi;
+        source_range(a[k], b[k], pd, d, &s_lo, &s_hi);
+        if (s_lo < pv_lo[k] || s_hi > pv_hi[k]) return fail(L.level, k);
+      }
+    }
+    // frames: a level whose source intervals (with the warp reach, data-dependent) do not fit every rank's slab
+    // is all-gathered, so on every level each rank's all-gather piece must come from its own frame slab;
+    // the finest level of a sharded solve must be reachable locally for the assumed reach
+    std::vector<size_t> Va(world), Vb(world);
+    for (int k = 0; k < world; ++k) {
+      size_t fa, fb;
+      flow3d_sharded_own_range(depth, k, world, &fa, &fb);
+      Va[k] = fa >= frame_ghost ? fa - frame_ghost : 0;
+      Vb[k] = std::min(depth, fb + frame_ghost);
+    }
+    if (world > 1) {
+      const float delta = (float)depth / (float)d;
+      std::vector<size_t> bounds(world + 1, d);
+      for (int k = 0; k < world; ++k) {
+        size_t fa, fb;
+        flow3d_sharded_own_range(depth, k, world, &fa, &fb);
+        size_t o = 0;
+        while (o < d && (long long)std::floor((float)o * delta) < (long long)fa) ++o;
+        bounds[k] = o;
+      }
+      bounds[0] = 0;
+      for (int k = 0; k < world; ++k) {
+        if (bounds[k + 1] <= bounds[k]) continue;
+        size_t s_lo, s_hi;
+        source_range(bounds[k], bounds[k + 1], depth, d, &s_lo, &s_hi);
+        if (s_lo < Va[k] || s_hi > Vb[k]) return fail(L.level, k);
+      }
+    }
+    for (int k = 0; k < world; ++k) {
+      const size_t m_lo = A[k] == 0 ? A[k] : A[k] + r2, m_hi = B[k] == d ? B[k] : B[k] - r2;
+      pv_lo[k] = m_lo;
+      pv_hi[k] = m_hi;
+    }
+    pd = d;
+    have_prev = true;
+  }
+  return FLOW3D_OK;
+}
+
+// Smallest frame ghost (32, 64, 128, ... capped at the depth = every rank holds the whole frames) the plan
+// accepts: the coarsest level's source interval is depth / level_depth planes long, which a deep or steep
+// pyramid (scale 0.9 x 40 levels: 61 planes; 0.5 x 7: 128) pushes past the default 32.
+size_t flow3d_sharded_frame_ghost(size_t width, size_t height, size_t depth, int world, const flow3d_params* p,
+                                  size_t min_planes_per_rank, size_t min_voxels_per_rank) {
+  if (!p || world < 1) return 0;
+  for (size_t g = std::min<size_t>(32, depth);; g = std::min(depth, 2 * g)) {
+    if (flow3d_sharded_plan_check(width, height, depth, world, p, min_planes_per_rank, min_voxels_per_rank, g, nullptr,
+                                  nullptr) == FLOW3D_OK)
+      return g;
+    if (g >= depth) return 0;
+  }
+}
+
 int flow3d_sharded_set_thresholds(flow3d_sharded* s, size_t min_planes_per_rank, size_t min_voxels_per_rank) {
   if (!s) return FLOW3D_ERR_NOT_INITIALIZED;
   s->min_planes = std::max<size_t>(min_planes_per_rank, 1);
@@ -865,6 +965,15 @@ int flow3d_sharded_compute(flow3d_sharded* s, const float* raw_0, const float* r
   if (!raw_0 || !raw_1 || !params || !flow_u || !flow_v || !flow_w || !out_a || !out_b) return FLOW3D_ERR_INVALID_ARG;
   if (ld < s->W || (ld & 3) || raw_z0 + raw_planes > s->D || raw_planes == 0) return FLOW3D_ERR_INVALID_ARG;
   if (params->warp_levels_count == 0 || params->median_radius == 0) return FLOW3D_ERR_INVALID_ARG;
+  {  // same verdict on every rank, before any of them enters a collective
+    int lv = -1, rk = -1;
+    if (flow3d_sharded_plan_check(s->W, s->H, s->D, s->world, params, s->min_planes, s->min_voxels, frame_ghost, &lv,
+                                  &rk) != FLOW3D_OK) {
+      std::fprintf(stderr, "flow3d_mgpu: %zux%zux%zu over %d ranks with %zu frame ghost planes cannot be partitioned "
+                   "(level %d, rank %d)\n", s->W, s->H, s->D, s->world, frame_ghost, lv, rk);
+      return FLOW3D_ERR_INVALID_ARG;
+    }
+  }
   M_CUDA(cudaSetDevice(s->device));
   s->st = reinterpret_cast<cudaStream_t>(stream);
   for (int i = 0; i < 7; ++i) s->stats[i] = 0;
@@ -947,7 +1056,9 @@ int flow3d_mgpu_compute_host(size_t W, size_t H, size_t D, int n_devices, const 
     for (int rc : rcs)
       if (rc != FLOW3D_OK) { release_group(); return rc; }
   }
-  const size_t ghost = std::min<size_t>(32, D);
+  const size_t ghost = flow3d_sharded_frame_ghost(W, H, D, n_devices, params, g_group->ranks[0]->min_planes,
+                                                  g_group->ranks[0]->min_voxels);
+  if (ghost == 0) return FLOW3D_ERR_INVALID_ARG;
   const size_t ld = flow3d_aligned_ld(W);
   std::vector<float> ms(n_devices, 0.f);
   std::vector<std::thread> th;

@@ -32,6 +32,9 @@ SIGNATURES = {
     "flow3d_sharded_compute": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(Params),
                                          C.c_size_t, _vp, _vp, _vp, C.c_size_t, _szp, _szp, _vp]),
     "flow3d_sharded_output_planes": (C.c_int, [_vp, C.POINTER(Params), _szp, _szp]),
+    "flow3d_sharded_plan_check": (C.c_int, [C.c_size_t] * 3 + [C.c_int, C.POINTER(Params), C.c_size_t, C.c_size_t, C.c_size_t,
+                                            C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "flow3d_sharded_frame_ghost": (C.c_size_t, [C.c_size_t] * 3 + [C.c_int, C.POINTER(Params), C.c_size_t, C.c_size_t]),
     "flow3d_sharded_set_thresholds": (C.c_int, [_vp, C.c_size_t, C.c_size_t]),
     "flow3d_sharded_set_profiling": (C.c_int, [_vp, C.c_int]),
     "flow3d_sharded_phase_ms": (C.c_int, [_vp, C.c_float * 9]),
@@ -77,6 +80,21 @@ def input_planes(depth, rank, world, sigma, frame_ghost):
     a, b = C.c_size_t(), C.c_size_t()
     load().flow3d_sharded_input_planes(depth, rank, world, sigma, frame_ghost, C.byref(a), C.byref(b))
     return int(a.value), int(b.value)
+
+
+def plan_check(W, H, D, world, params=None, min_planes=12, min_voxels=1 << 18, frame_ghost=32):
+    """host-only dry run of the partition arithmetic; returns (ok, bad_level, bad_rank)"""
+    p = make_params(params)
+    bl, br = C.c_int(-1), C.c_int(-1)
+    rc = load().flow3d_sharded_plan_check(W, H, D, world, C.byref(p), min_planes, min_voxels, frame_ghost,
+                                          C.byref(bl), C.byref(br))
+    return rc == 0, int(bl.value), int(br.value)
+
+
+def frame_ghost(W, H, D, world, params=None, min_planes=12, min_voxels=1 << 18):
+    """smallest frame ghost (planes) the sharded solve of this geometry needs; 0 = cannot be partitioned"""
+    p = make_params(params)
+    return int(load().flow3d_sharded_frame_ghost(W, H, D, world, C.byref(p), min_planes, min_voxels))
 
 
 class ShardedSolver:

@@ -65,6 +65,23 @@ int flow3d_sharded_compute(flow3d_sharded* s, const float* raw_0, const float* r
  * FLOW3D_MGPU_MIN_VOXELS. */
 int flow3d_sharded_set_thresholds(flow3d_sharded* s, size_t min_planes_per_rank, size_t min_voxels_per_rank);
 
+/* Host-only dry run (no device, no communicator) of the partition arithmetic flow3d_sharded_compute relies on,
+ * for every level and every rank of a `world`-rank solve: prolongation sources inside the previous level's
+ * valid planes, matching ghost-exchange sizes between neighbours, every rank's piece of an all-gathered level
+ * frame inside its own frame slab (own planes +- frame_ghost).  FLOW3D_OK, or FLOW3D_ERR_INVALID_ARG with the
+ * first offending level / rank (either may be NULL).  flow3d_sharded_compute runs the same check before it
+ * touches the device, so an unsupported geometry fails identically on every rank instead of leaving the others
+ * inside a collective. */
+int flow3d_sharded_plan_check(size_t width, size_t height, size_t depth, int world, const flow3d_params* params,
+                              size_t min_planes_per_rank, size_t min_voxels_per_rank, size_t frame_ghost,
+                              int* bad_level, int* bad_rank);
+
+/* smallest frame_ghost (32, 64, ... up to the depth) for which flow3d_sharded_plan_check accepts the solve; 0 if
+ * none does.  32 planes cover the default pyramid (scale 0.95: 40 levels need 8, 60 levels 22); steeper or
+ * deeper pyramids need more (scale 0.9 x 40 levels: 61).  flow3d_mgpu_compute_host uses it. */
+size_t flow3d_sharded_frame_ghost(size_t width, size_t height, size_t depth, int world, const flow3d_params* params,
+                                  size_t min_planes_per_rank, size_t min_voxels_per_rank);
+
 /* planes [*a, *b) flow3d_sharded_compute will deliver on this rank for these parameters (the owned range
  * of the finest level, or [0, D) when that level is too small to shard) */
 int flow3d_sharded_output_planes(const flow3d_sharded* s, const flow3d_params* params, size_t* a, size_t* b);

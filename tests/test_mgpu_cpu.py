@@ -46,3 +46,49 @@ def test_input_planes_cover_own_range_plus_ghost_and_blur():
             a, b = m.own_range(1024, rank, world)
             lo, hi = m.input_planes(1024, rank, world, 2.0, 32)
             assert lo == max(0, a - 38) and hi == min(1024, b + 38)
+
+
+@pytest.mark.parametrize("shape,world,levels", [
+    ((1024, 1024, 1024), 2, 40), ((1024, 1024, 1024), 8, 40), ((1024, 1024, 1024), 4, 40),
+    ((2048, 2048, 2048), 8, 60), ((512, 512, 512), 2, 40), ((512, 512, 512), 8, 40),
+    ((584, 388, 5), 2, 40), ((128, 128, 128), 3, 40), ((487, 301, 233), 5, 25),
+    ((256, 256, 256), 2, 40), ((256, 256, 256), 4, 40), ((256, 256, 256), 8, 40),  # bench.py's N>1 parity pair
+])
+def test_plan_check_accepts_the_bench_geometries(shape, world, levels):
+    """the partition arithmetic of the sharded solve (prolongation sources inside the previous level's valid
+    planes, matching ghost sizes, all-gather pieces inside a rank's own frame slab) on every level and rank of
+    the configurations bench.py and the GPU tests run (host-only dry run: no device)"""
+    import cuda_flow3d_b200.mgpu as m
+    ok, lv, rk = m.plan_check(*shape, world, {"warp_levels_count": levels})
+    assert ok, "level %d rank %d" % (lv, rk)
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_plan_check_with_test_thresholds(world):
+    """the lowered thresholds the GPU tests use to shard small volumes"""
+    import cuda_flow3d_b200.mgpu as m
+    for shape in ((64, 48, 96), (40, 36, 120), (33, 47, 150)):
+        ok, lv, rk = m.plan_check(*shape, world, {"warp_levels_count": 12}, min_planes=2, min_voxels=1)
+        assert ok, "%s level %d rank %d" % (shape, lv, rk)
+    # tests/test_mgpu_gpu.py: (W, H, D) = (72, 40, 48 * world), 14 levels, thresholds 8 / 1, 16 ghost planes
+    ok, lv, rk = m.plan_check(72, 40, 48 * world, world, {"warp_levels_count": 14}, min_planes=8, min_voxels=1,
+                              frame_ghost=16)
+    assert ok, "level %d rank %d" % (lv, rk)
+
+
+def test_plan_check_reports_a_frame_ghost_too_small_for_a_gathered_level():
+    import cuda_flow3d_b200.mgpu as m
+    # ghost of 0 planes: a coarse level's source interval (1/0.95^k planes long) reaches past the rank's slab
+    ok, lv, rk = m.plan_check(256, 256, 256, 4, {"warp_levels_count": 40}, frame_ghost=0)
+    assert not ok and lv >= 0 and 0 <= rk < 4
+
+
+def test_frame_ghost_grows_with_the_coarsest_source_interval():
+    import cuda_flow3d_b200.mgpu as m
+    assert m.frame_ghost(1024, 1024, 1024, 8) == 32                             # default pyramid
+    assert m.frame_ghost(2048, 2048, 2048, 8, {"warp_levels_count": 60}) == 32  # BASELINE configs[4]
+    g = m.frame_ghost(512, 512, 512, 4, {"warp_scale_factor": 0.9})             # coarsest interval: 61 planes
+    assert g == 64 and m.plan_check(512, 512, 512, 4, {"warp_scale_factor": 0.9}, frame_ghost=g)[0]
+    assert not m.plan_check(512, 512, 512, 4, {"warp_scale_factor": 0.9}, frame_ghost=32)[0]
+    assert m.frame_ghost(300, 200, 40, 2, {"warp_scale_factor": 0.5, "warp_levels_count": 10}) <= 40  # capped at the depth
+    assert m.frame_ghost(64, 64, 64, 1) == 32
