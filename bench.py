@@ -34,10 +34,12 @@ SEED = 20240521
 _REAL_STDOUT = None
 
 
-def workload_name(n):
-    """ONE string for both arms (the driver compares config.workload of the two lines)"""
-    return ("synthetic %d^3 pair with known rigid motion (BASELINE configs[2]), default parameters: "
-            "warp_levels_count 40, scale 0.95, 40 outer x 5 inner sweeps, median 5, sigma 2" % n)
+def workload_name(n, levels=40):
+    """ONE string for both arms at every N (the driver compares config.workload of the two lines); how the
+    volume is spread over GPUs is config.parallelism, not the workload"""
+    cfg = 4 if n >= 2048 else (3 if n >= 1024 else 2)
+    return ("synthetic %d^3 pair with known rigid motion (BASELINE configs[%d]), default parameters: "
+            "warp_levels_count %d, scale 0.95, 40 outer x 5 inner sweeps, median 5, sigma 2" % (n, cfg, levels))
 
 
 def sha256_file(path, chunk=1 << 24):
@@ -257,11 +259,20 @@ def run_reference(args, rank, world):
         return
     import shutil
     from oracle import ref_runner
-    n = args.size or 512
+    # the workload is our arm's at this N (N = 1: 512^3, N > 1: the 1024^3 volume that arm shards); each step is
+    # one full default solve of a BOUNDED SAMPLE of it -- the same generator at <= 512^3 -- because one reference
+    # solve of 1024^3 takes ~3.5 min (8x the voxels at 5 Mvoxel/s); the metric is a per-voxel rate
+    ng = max(world, args.gpus)
+    n_work = args.size or (512 if ng <= 1 else 1024)
+    n = min(n_work, 512)
+    levels = args.warp_levels if (ng > 1 and args.warp_levels > 0) else 40
     base = {"impl": "reference", "metric": "Mvoxel/s per full pyramid flow solve", "unit": "Mvoxel/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
-            "dtype": "f32", "data": "synthetic", "scaling": "weak", "vs_baseline": None,
-            "config": {"workload": workload_name(n), "parallelism": "1 GPU",
+            "dtype": "f32", "data": "synthetic", "scaling": "weak" if ng <= 1 else "strong", "vs_baseline": None,
+            "config": {"workload": workload_name(n_work, levels),
+                       "parallelism": "1 GPU" if ng <= 1 else "1 GPU (the reference has no multi-GPU path)",
+                       "step_sample": "one full default solve of the %d^3 pair of the same generator%s" %
+                                      (n, "" if n == n_work else " (1/%d of the workload's voxels; rate metric)" % ((n_work // n) ** 3)),
                        "inputs_larger_than_l2": bool(n ** 3 * 4 > 126e6)}}
     gen = os.path.join(ROOT, "build", "flow3d_synth")
     if not ref_runner.available():
@@ -572,14 +583,12 @@ def run_sharded(args, rank, world, local_rank):
             "metric": "Mvoxel/s per full pyramid flow solve", "value": value, "unit": "Mvoxel/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "synthetic %d^3 pair with known rigid motion (BASELINE configs[%d]) z-sharded over %d "
-                                   "GPUs, default parameters: warp_levels_count %d, scale 0.95, 40 outer x 5 inner sweeps, "
-                                   "median 5, sigma 2" % (n, 4 if n >= 2048 else 3, world, P["warp_levels_count"]),
-                       "parallelism": "z-slabs, %d ghost planes, C++ sharded solver (libflow3d_b200_mgpu.so): one grouped "
+            "config": {"workload": workload_name(n, P["warp_levels_count"]),
+                       "parallelism": "ONE volume z-sharded over %d GPUs: z-slabs, %d ghost planes, C++ sharded solver (libflow3d_b200_mgpu.so): one grouped "
                                       "ncclSend/ncclRecv of the ghost planes per outer iteration on the solve's stream; "
                                       "frames sharded too (coarse level frames assembled by all-gather); levels too thin "
                                       "to shard are computed by every rank (replicated, not gathered to one GPU: same "
-                                      "wall time, no scatter)" % (P["inner_iterations_count"] + 1),
+                                      "wall time, no scatter)" % (world, P["inner_iterations_count"] + 1),
                        "pyramid_levels": nlev, "level_voxels": nsum, "inputs_larger_than_l2": True,
                        "sharded_levels_per_step": stats.get("sharded_levels", 0) / max(1, args.steps),
                        "replicated_levels_per_step": stats.get("replicated_levels", 0) / max(1, args.steps),
