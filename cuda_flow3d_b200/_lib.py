@@ -111,6 +111,7 @@ SIGNATURES = {
     "flow3d_solver_compute_device": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.POINTER(Params), _vp, _vp,
                                                _vp, _vp]),
     "flow3d_solver_tune": (C.c_int, [_vp, C.POINTER(Params)]),
+    "flow3d_set_pdl": (C.c_int, [C.c_int]),
     "flow3d_tune_kernels": (C.c_int, [_sz3, C.c_size_t, C.POINTER(ZSlab), _f3, _vp, C.c_size_t, _vp]),
     "flow3d_tune_query": (C.c_int, [C.c_int, _sz3, C.c_size_t, C.POINTER(ZSlab), C.c_int * 3]),
     "flow3d_solver_last_timing": (C.c_int, [_vp, C.c_float * 2]),

@@ -199,6 +199,9 @@ static int solve_level(const float* fx, const float* fy, const float* fz, const 
                        size_t* outer_done = nullptr) {
   const size_t bytes = (size_t)g.ps * g.d * sizeof(float);
   const double nvox = (double)g.w * g.h * g.d;
+  // the phi / sweep launches below form one dependent chain on `st`: launched as programmatic dependents
+  // (common.cuh; FLOW3D_PDL=0 turns it off), which hides the launch gap that dominates the small levels
+  PdlScope pdl_chain(true);
   if (tm) tm->mark(FLOW3D_STAGE_UPDATE, st);
   // cuda_operation_solve.cpp:183-188
   F3D_CUDA(cudaMemsetAsync(du, 0, bytes, st));
@@ -1079,6 +1082,8 @@ static int solver_tune(flow3d_solver* s, const flow3d_params* p, bool quick) {
 }
 
 int flow3d_solver_tune(flow3d_solver* s, const flow3d_params* p) { return solver_tune(s, p, false); }
+
+int flow3d_set_pdl(int mode) { return pdl_set_mode(mode); }
 
 size_t flow3d_update_norm_workspace_bytes(void) { return update_norm_workspace_bytes(); }
 

@@ -8,6 +8,7 @@
 // (z-marching warps, vector loads, register-rotated z neighbours, shuffle x neighbours, per-level
 // precomputed image derivatives) is new.  A sensitivity study shows that merely changing
 // FMA contraction moves the final 128^3 flow by up to 9e-3 voxel, so this is what the 1e-3 gate needs.
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <map>
@@ -414,6 +415,8 @@ __device__ __forceinline__ void sweep_march1(const SweepArgs& a, const Dims& g, 
 
 template <int VEC, int MINB, int ROT, int SPEC, bool KSI = false>
 __global__ void __launch_bounds__(128, MINB) sweep_kernel(const SweepArgs a) {
+  pdl_trigger();  // the next launch of the chain may become resident while this grid drains ...
+  pdl_wait();     // ... and this one touches memory only after its predecessor has completed (common.cuh)
   const Dims g = a.g;
   const LaneMap lm = lane_map<VEC>(a.lpr, g.w, g.h, a.wx);
   if (lm.first_row >= g.h || lm.tile_x * a.lpr * VEC >= g.w) return;  // whole warp leaves together
@@ -458,6 +461,29 @@ __global__ void __launch_bounds__(128, MINB) sweep_kernel(const SweepArgs a) {
     else sweep_march1<VEC, false, KSI>(a, g, c, z_begin, z_end);
   }
 }
+
+static thread_local bool g_pdl_active = false;
+static std::atomic<bool> g_pdl_refused{false};
+static std::atomic<int> g_pdl_mode{-1};  // -1: $FLOW3D_PDL (default on), 0 off, 1 on  (flow3d_set_pdl)
+static bool pdl_env_default() {
+  static const bool enabled = [] {
+    const char* e = getenv("FLOW3D_PDL");
+    return !(e && *e) || atoi(e) != 0;
+  }();
+  return enabled;
+}
+bool pdl_wanted() {
+  const int m = g_pdl_mode.load(std::memory_order_relaxed);
+  return (m < 0 ? pdl_env_default() : m != 0) && !g_pdl_refused.load(std::memory_order_relaxed);
+}
+int pdl_set_mode(int mode) {
+  g_pdl_mode.store(mode < 0 ? -1 : (mode != 0), std::memory_order_relaxed);
+  return pdl_wanted() ? 1 : 0;
+}
+bool pdl_active() { return g_pdl_active && pdl_wanted(); }
+void pdl_disable() { g_pdl_refused.store(true, std::memory_order_relaxed); }
+PdlScope::PdlScope(bool on) : prev(g_pdl_active) { g_pdl_active = on; }
+PdlScope::~PdlScope() { g_pdl_active = prev; }
 
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
@@ -738,21 +764,21 @@ static int launch_sweep_cfg(SweepArgs a, const Dims& g, ZRange zr, TuneCfg cfg, 
             cfg.nchunks > 0 ? chunk_len(zr.end - zr.begin, cfg.nchunks) : 0);
   static const int rot = env_int("FLOW3D_SWEEP_ROT", 0), spec = env_int("FLOW3D_SWEEP_SPEC", 0);
   if (a.oksi) {  // first sweep of an outer iteration: computes and stores ksi
-    if (vec == 4) sweep_kernel<4, 2, 0, 0, true><<<grid, block, 0, st>>>(a);
-    else if (vec == 2) sweep_kernel<2, 4, 0, 0, true><<<grid, block, 0, st>>>(a);
-    else sweep_kernel<1, 4, 0, 0, true><<<grid, block, 0, st>>>(a);
+    if (vec == 4) launch_chain_kernel(sweep_kernel<4, 2, 0, 0, true>, grid, block, st, a);
+    else if (vec == 2) launch_chain_kernel(sweep_kernel<2, 4, 0, 0, true>, grid, block, st, a);
+    else launch_chain_kernel(sweep_kernel<1, 4, 0, 0, true>, grid, block, st, a);
     count_launch();
     return check_launch("sweep_kernel<KSI>");
   }
   if (vec == 4) {
-    if (rot && spec) sweep_kernel<4, 2, 1, 1><<<grid, block, 0, st>>>(a);
-    else if (rot) sweep_kernel<4, 2, 1, 0><<<grid, block, 0, st>>>(a);
-    else if (spec) sweep_kernel<4, 2, 0, 1><<<grid, block, 0, st>>>(a);
-    else sweep_kernel<4, 2, 0, 0><<<grid, block, 0, st>>>(a);
+    if (rot && spec) launch_chain_kernel(sweep_kernel<4, 2, 1, 1>, grid, block, st, a);
+    else if (rot) launch_chain_kernel(sweep_kernel<4, 2, 1, 0>, grid, block, st, a);
+    else if (spec) launch_chain_kernel(sweep_kernel<4, 2, 0, 1>, grid, block, st, a);
+    else launch_chain_kernel(sweep_kernel<4, 2, 0, 0>, grid, block, st, a);
   } else if (vec == 2) {
-    sweep_kernel<2, 4, 0, 0><<<grid, block, 0, st>>>(a);
+    launch_chain_kernel(sweep_kernel<2, 4, 0, 0>, grid, block, st, a);
   } else {
-    sweep_kernel<1, 4, 0, 0><<<grid, block, 0, st>>>(a);
+    launch_chain_kernel(sweep_kernel<1, 4, 0, 0>, grid, block, st, a);
   }
   count_launch();
   return check_launch("sweep_kernel");
@@ -1025,6 +1051,8 @@ __device__ __forceinline__ void phi_ksi_body(const PhiKsiArgs& a, const LaneMap&
 template <int VEC, bool WITH_KSI = true>
 __global__ void __launch_bounds__(128) phi_ksi_kernel(const PhiKsiArgs a, int zchunk, int pf, int zs, int ze,
                                                       int lpr) {
+  pdl_trigger();
+  pdl_wait();
   const LaneMap lm = lane_map<VEC>(lpr, a.g.w, a.g.h);
   if (lm.first_row >= a.g.h) return;
   const int tx0 = lm.tile_x * lpr * VEC, tx1 = tx0 + lpr * VEC;
@@ -1042,12 +1070,12 @@ static int launch_phi_ksi_cfg(const PhiKsiArgs& a, const Dims& g, ZRange zr, Tun
   const int lpr = (forced_lpr == 8 || forced_lpr == 16 || forced_lpr == 32) ? forced_lpr : pick_lpr(g.w, vec);
   pick_grid(g, zr, vec, lpr, 4, grid, block, zchunk, 1, 5, cfg.nchunks > 0 ? chunk_len(zr.end - zr.begin, cfg.nchunks) : 0);
   if (!a.ksi) {
-    if (vec == 4) phi_ksi_kernel<4, false><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end, lpr);
-    else if (vec == 2) phi_ksi_kernel<2, false><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end, lpr);
-    else phi_ksi_kernel<1, false><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end, lpr);
-  } else if (vec == 4) phi_ksi_kernel<4><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end, lpr);
-  else if (vec == 2) phi_ksi_kernel<2><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end, lpr);
-  else phi_ksi_kernel<1><<<grid, block, 0, st>>>(a, zchunk, pf, zr.begin, zr.end, lpr);
+    if (vec == 4) launch_chain_kernel(phi_ksi_kernel<4, false>, grid, block, st, a, zchunk, pf, zr.begin, zr.end, lpr);
+    else if (vec == 2) launch_chain_kernel(phi_ksi_kernel<2, false>, grid, block, st, a, zchunk, pf, zr.begin, zr.end, lpr);
+    else launch_chain_kernel(phi_ksi_kernel<1, false>, grid, block, st, a, zchunk, pf, zr.begin, zr.end, lpr);
+  } else if (vec == 4) launch_chain_kernel(phi_ksi_kernel<4>, grid, block, st, a, zchunk, pf, zr.begin, zr.end, lpr);
+  else if (vec == 2) launch_chain_kernel(phi_ksi_kernel<2>, grid, block, st, a, zchunk, pf, zr.begin, zr.end, lpr);
+  else launch_chain_kernel(phi_ksi_kernel<1>, grid, block, st, a, zchunk, pf, zr.begin, zr.end, lpr);
   count_launch();
   return check_launch("phi_ksi_kernel");
 }

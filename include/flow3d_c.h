@@ -289,6 +289,13 @@ int flow3d_tune_kernels(const size_t dims[3], size_t ld, const flow3d_zslab* sla
  * out = {voxels per lane, z chunks, variant (0 register-marching, 1/2 TMA tiles 64x8 / 32x16)}, 0 if none */
 int flow3d_tune_query(int kernel, const size_t dims[3], size_t ld, const flow3d_zslab* slab, int out[3]);
 
+/* Programmatic dependent launch of a level's phi / sweep chain (flow3d_solve_level and the solver object's
+ * solves): each of the 6 x outer launches may become resident while its predecessor drains and waits on the
+ * device for it to complete -- same kernels, same bits, shorter launch gaps on the small levels.
+ * mode 1 = on, 0 = off, -1 = the environment's choice ($FLOW3D_PDL, default on).  Returns the mode in effect
+ * (0 also when the driver refused a launch with the attribute and the library fell back). */
+int flow3d_set_pdl(int mode);
+
 /* milliseconds of the last compute call, measured with CUDA events: [0] whole call (host call:
  * including H2D/D2H, the reference's own bracket optical_flow_e.cpp:169->579), [1] device-only */
 int flow3d_solver_last_timing(const flow3d_solver* s, float ms[2]);

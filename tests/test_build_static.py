@@ -61,3 +61,27 @@ def test_constant_division_sequence_is_exact(tmp_path):
     r = subprocess.run([exe, "12", "7"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "mismatches=0" in r.stdout
+
+
+def test_pdl_chain_kernels_wait_before_touching_global_memory():
+    """Kernels that solve_level launches as programmatic dependents (common.cuh: launch_chain_kernel) may become
+    resident while their predecessor still runs: each must execute griddepcontrol.wait (SASS: ACQBULK) before
+    its first global load, store or prefetch.  Checked on the SASS of every instance of the two chain kernels."""
+    obj = os.path.join(CSRC, "kernels_solve.o")
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if not (os.path.exists(obj) and os.path.exists(cuobjdump)):
+        pytest.skip("no object file / cuobjdump")
+    sass = subprocess.run([cuobjdump, "-sass", obj], capture_output=True, text=True, timeout=600).stdout
+    funcs = re.split(r"\n\s*Function : ", sass)[1:]
+    checked = 0
+    for f in funcs:
+        name = f.split("\n", 1)[0].strip()
+        if not re.search(r"sweep_kernel|phi_ksi_kernel", name):
+            continue
+        ops = re.findall(r"/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", f)
+        assert "ACQBULK" in ops and "PREEXIT" in ops, name
+        first_wait = ops.index("ACQBULK")
+        mem = [i for i, o in enumerate(ops) if re.match(r"(LDG|STG|LD\b|ST\b|CCTL|ATOM|RED|LDGSTS|UTMA)", o)]
+        assert mem and min(mem) > first_wait, "%s touches global memory before ACQBULK" % name
+        checked += 1
+    assert checked >= 12
