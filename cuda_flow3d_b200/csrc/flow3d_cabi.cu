@@ -200,8 +200,13 @@ static int solve_level(const float* fx, const float* fy, const float* fz, const 
   const size_t bytes = (size_t)g.ps * g.d * sizeof(float);
   const double nvox = (double)g.w * g.h * g.d;
   // the phi / sweep launches below form one dependent chain on `st`: launched as programmatic dependents
-  // (common.cuh; FLOW3D_PDL=0 turns it off), which hides the launch gap that dominates the small levels
-  PdlScope pdl_chain(true);
+  // (common.cuh; FLOW3D_PDL=0 turns it off), which hides the launch gap that is a visible share of the 5-150 us
+  // kernels of the small levels; the large levels (gap < 1 % of a launch) keep the ordinary launches
+  static const double pdl_max_voxels = [] {
+    const char* e = getenv("FLOW3D_PDL_MAX_VOXELS");
+    return (e && *e) ? atof(e) : 33554432.0;  // 2^25 ~ 322^3
+  }();
+  PdlScope pdl_chain(nvox <= pdl_max_voxels);
   if (tm) tm->mark(FLOW3D_STAGE_UPDATE, st);
   // cuda_operation_solve.cpp:183-188
   F3D_CUDA(cudaMemsetAsync(du, 0, bytes, st));
