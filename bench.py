@@ -366,7 +366,9 @@ def run_sharded(args, rank, world, local_rank):
     ld = int(L.flow3d_aligned_ld(W))
     st = torch.cuda.current_stream()
     sp = C.c_void_p(st.cuda_stream)
-    ghost = 32
+    # frame ghost planes per rank: 32 for the default pyramid (what every record in profiles/ ran with); a deeper
+    # pyramid (--warp-levels 80 at 2048^3: coarsest source interval 57 planes) needs more
+    ghost = max(32, mgpu.frame_ghost(n, n, n, world, P))
 
     def barrier():
         dist.barrier()

@@ -92,3 +92,8 @@ def test_frame_ghost_grows_with_the_coarsest_source_interval():
     assert not m.plan_check(512, 512, 512, 4, {"warp_scale_factor": 0.9}, frame_ghost=32)[0]
     assert m.frame_ghost(300, 200, 40, 2, {"warp_scale_factor": 0.5, "warp_levels_count": 10}) <= 40  # capped at the depth
     assert m.frame_ghost(64, 64, 64, 1) == 32
+    # bench.py N>1: default runs keep the 32 planes every recorded run used; the parity pair (thresholds 8 / 1) too
+    for world in (2, 4, 8):
+        assert m.frame_ghost(1024, 1024, 1024, world) == 32
+        assert m.frame_ghost(256, 256, 256, world, None, 8, 1) == 32
+    assert m.frame_ghost(2048, 2048, 2048, 8, {"warp_levels_count": 80}) == 64
