@@ -107,3 +107,29 @@ def test_data3d_raw_roundtrip(tmp_path):
     assert np.array_equal(e.DataPtr(), np.clip(d.DataPtr(), 0, 255).astype(np.uint8).astype(np.float32))
     assert not e.ReadRAWFromFileF32(f32, 5, 4, 4)  # size mismatch is an error (data3d.cpp:124-131)
     assert not e.ReadRAWFromFileU8(str(tmp_path / "missing.raw"), 5, 4, 3)
+
+
+def test_max_warp_level_equals_the_reference_function(lib):
+    """flow3d_max_warp_level against the REFERENCE's own OpticalFlowBase::GetMaxWarpLevel
+    (src/optical_flow/optical_flow_base.cpp:31-56) on 31 449 (W, H, D, scale) cases: the golden table was printed
+    by the reference function itself, compiled from /root/reference (scripts/make_levels_golden.sh).  The count
+    decides the level list of every solve, so it has to agree exactly -- including scale >= 1 and dims < 4."""
+    import ctypes as C
+    import lzma
+    import struct
+    path = os.path.join(ROOT, "tests", "golden", "max_warp_level.txt.xz")
+    lib.flow3d_max_warp_level.restype = C.c_size_t
+    lib.flow3d_max_warp_level.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t, C.c_float]
+    n = bad = 0
+    first = None
+    with lzma.open(path, "rt") as f:
+        for line in f:
+            w, h, d, bits, want = (int(x) for x in line.split())
+            scale = struct.unpack("<f", struct.pack("<I", bits))[0]
+            got = int(lib.flow3d_max_warp_level(w, h, d, scale))
+            n += 1
+            if got != want:
+                bad += 1
+                first = first or (w, h, d, scale, want, got)
+    assert n > 30000
+    assert bad == 0, "%d of %d differ; first: %s" % (bad, n, first)

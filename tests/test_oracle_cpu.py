@@ -83,3 +83,23 @@ def test_oracle_recovers_a_translation(oracle):
     assert abs(u[inner].mean() - 0.8) < 0.15
     assert abs(v[inner].mean() + 0.5) < 0.15
     assert abs(w_[inner].mean() - 0.3) < 0.15
+
+
+def test_oracle_level_count_equals_the_reference_function(oracle):
+    """the oracle's level count against the table printed by the reference's own GetMaxWarpLevel
+    (tests/golden/max_warp_level.txt.xz, scripts/make_levels_golden.sh): pins the oracle's schedule to the
+    reference's code, not to a reading of it"""
+    import lzma
+    import os
+    import struct
+    from conftest import ROOT
+    bad = n = 0
+    with lzma.open(os.path.join(ROOT, "tests", "golden", "max_warp_level.txt.xz"), "rt") as f:
+        for i, line in enumerate(f):
+            if i % 3:
+                continue
+            w, h, d, bits, want = (int(x) for x in line.split())
+            scale = struct.unpack("<f", struct.pack("<I", bits))[0]
+            n += 1
+            bad += int(oracle.max_warp_level(w, h, d, scale) != want)
+    assert n > 10000 and bad == 0
