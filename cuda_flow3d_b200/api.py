@@ -99,6 +99,9 @@ class Data3D:
         return self._a[z, y, x]
 
     def Swap(self, other):
+        if self._a.shape != other._a.shape:  # data3d.cpp:44-52: same-shape volumes only
+            print("Error. Cannot swap two Data3D objects (wrong dimensions).")
+            return
         self._a, other._a = other._a, self._a
 
     def ZeroData(self):
@@ -123,8 +126,9 @@ class Data3D:
         return self._read(filename, width, height, depth, np.float32)
 
     def WriteRAWToFileU8(self, filename):
-        # data3d.cpp:189-190: clamp to [0,255] then truncate
-        np.clip(self._a, 0, 255).astype(np.uint8).tofile(filename)
+        # data3d.cpp:189-190: min(255, max(0, x)) then truncate; std::max(0.f, NaN) keeps the 0
+        a = np.where(np.isnan(self._a), np.float32(0), self._a)
+        np.clip(a, 0, 255).astype(np.uint8).tofile(filename)
         return True
 
     def WriteRAWToFileF32(self, filename):

@@ -57,3 +57,28 @@ def test_u8_fixture_shows_clamp_truncate_and_nan_rule():
     b = open(os.path.join(GOLD, "out_u8.raw"), "rb").read()
     assert len(b) == 7 * 5 * 3
     assert list(b[:12]) == [0, 0, 127, 254, 255, 255, 0, 0, 255, 0, 0, 1]
+
+
+def test_python_mirror_writes_the_same_files(tmp_path, capsys):
+    """cuda_flow3d_b200.api.Data3D (the ctypes-side mirror tests and bench.py use) against the same golden files"""
+    import numpy as np
+    from cuda_flow3d_b200.api import Data3D
+    W, H, D = 7, 5, 3
+    a = Data3D()
+    assert a.ReadRAWFromFileF32(os.path.join(GOLD, "out_f32.raw"), W, H, D)
+    assert a.WriteRAWToFileU8(str(tmp_path / "u8.raw")) and a.WriteRAWToFileF32(str(tmp_path / "f32.raw"))
+    assert open(tmp_path / "u8.raw", "rb").read() == open(os.path.join(GOLD, "out_u8.raw"), "rb").read()
+    assert open(tmp_path / "f32.raw", "rb").read() == open(os.path.join(GOLD, "out_f32.raw"), "rb").read()
+    b = Data3D()
+    assert b.ReadRAWFromFileU8(os.path.join(GOLD, "out_u8.raw"), W, H, D)
+    assert b.DataPtr().tobytes() == open(os.path.join(GOLD, "reread_u8_as_f32.raw"), "rb").read()
+    ref = json.load(open(os.path.join(GOLD, "results.json")))
+    c = Data3D()
+    assert c.ReadRAWFromFileU8(os.path.join(GOLD, "out_u8.raw"), W, H, D + 1) == bool(ref["read_u8_file_too_short"])
+    assert c.ReadRAWFromFileU8(os.path.join(GOLD, "out_u8.raw"), W, H, D - 1) == bool(ref["read_u8_file_too_long"])
+    assert c.ReadRAWFromFileF32(os.path.join(GOLD, "out_f32.raw"), W + 1, H, D) == bool(ref["read_f32_file_too_short"])
+    assert c.ReadRAWFromFileF32(os.path.join(GOLD, "out_f32.raw"), W, H - 1, D) == bool(ref["read_f32_file_too_long"])
+    assert c.ReadRAWFromFileU8(str(tmp_path / "missing.raw"), W, H, D) == bool(ref["read_missing_file"])
+    small = Data3D(2, 2, 2)
+    small.Swap(a)
+    assert small.Width() == 2 and a.Width() == W and "Cannot swap" in capsys.readouterr().out
