@@ -112,6 +112,7 @@ SIGNATURES = {
                                                _vp, _vp]),
     "flow3d_solver_tune": (C.c_int, [_vp, C.POINTER(Params)]),
     "flow3d_set_pdl": (C.c_int, [C.c_int]),
+    "flow3d_gauss_taps": (C.c_int, [C.c_float, C.POINTER(C.c_float), C.c_size_t, C.POINTER(C.c_size_t)]),
     "flow3d_tune_kernels": (C.c_int, [_sz3, C.c_size_t, C.POINTER(ZSlab), _f3, _vp, C.c_size_t, _vp]),
     "flow3d_tune_query": (C.c_int, [C.c_int, _sz3, C.c_size_t, C.POINTER(ZSlab), C.c_int * 3]),
     "flow3d_solver_last_timing": (C.c_int, [_vp, C.c_float * 2]),

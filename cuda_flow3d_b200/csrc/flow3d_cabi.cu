@@ -1090,6 +1090,17 @@ int flow3d_solver_tune(flow3d_solver* s, const flow3d_params* p) { return solver
 
 int flow3d_set_pdl(int mode) { return pdl_set_mode(mode); }
 
+int flow3d_gauss_taps(float sigma, float* taps, size_t capacity, size_t* radius) {
+  if (!taps || !radius || !(sigma > 0.f)) return FLOW3D_ERR_INVALID_ARG;
+  float t[2 * 32 + 1];
+  const int r = gauss_taps(sigma, t, 32);
+  if (r < 0) return FLOW3D_ERR_UNSUPPORTED;
+  if (capacity < (size_t)(2 * r + 1)) return FLOW3D_ERR_INVALID_ARG;
+  for (int i = 0; i < 2 * r + 1; ++i) taps[i] = t[i];
+  *radius = (size_t)r;
+  return FLOW3D_OK;
+}
+
 size_t flow3d_update_norm_workspace_bytes(void) { return update_norm_workspace_bytes(); }
 
 int flow3d_update_norm(const float* a0, const float* a1, const float* a2, const float* b0,

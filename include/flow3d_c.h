@@ -178,6 +178,14 @@ int flow3d_add3(float* u, float* v, float* w, const float* du, const float* dv, 
 int flow3d_median(const float* in, float* out, const size_t dims[3], size_t ld, size_t radius,
                   void* stream);
 
+/* Host only: the taps flow3d_gauss_blur uses for `sigma` -- CudaOperationConvolution3D::ComputeGaussianKernel
+ * with precision 3 and pixel size 1.0 as Execute() calls it
+ * (src/cuda_operations/entire_data/cuda_operation_convolution.cpp:85-108, :159): radius (size_t)(3*sigma),
+ * 2*radius+1 taps.  Returns FLOW3D_ERR_UNSUPPORTED if the radius exceeds 32 (the kernels' limit) or
+ * FLOW3D_ERR_INVALID_ARG if `capacity` floats cannot hold the taps.  Checked against the reference's own function
+ * by tests/test_cabi_cpu.py. */
+int flow3d_gauss_taps(float sigma, float* taps, size_t capacity, size_t* radius);
+
 /* ---- z-slab (multi-GPU) variants: identical arithmetic, boundary handling per flow3d_zslab ------ */
 /* pre-blur of a z-slab of the full-resolution frame: zero padding at the global faces only; the
  * slab must hold (size_t)(3*sigma) ghost planes around [z_begin, z_end) (or reach a global face);

@@ -133,3 +133,30 @@ def test_max_warp_level_equals_the_reference_function(lib):
                 first = first or (w, h, d, scale, want, got)
     assert n > 30000
     assert bad == 0, "%d of %d differ; first: %s" % (bad, n, first)
+
+
+def test_gauss_taps_equal_the_reference_function(lib, oracle):
+    """the blur taps of the library (flow3d_gauss_taps) and of the oracle against the REFERENCE's own
+    ComputeGaussianKernel (cuda_operation_convolution.cpp:85-108): tests/golden/gauss_taps.txt was printed by
+    that function, compiled from /root/reference (scripts/make_taps_golden.sh).  Bit-exact, radius included."""
+    import ctypes as C
+    import struct
+    n = 0
+    for line in open(os.path.join(ROOT, "tests", "golden", "gauss_taps.txt")):
+        v = [int(x) for x in line.split()]
+        sigma = struct.unpack("<f", struct.pack("<I", v[0]))[0]
+        radius, want = v[1], v[2:]
+        assert len(want) == 2 * radius + 1
+        o_taps, o_r = oracle.gauss_taps(sigma)
+        assert o_r == radius and [int(x) for x in o_taps.view(np.uint32)] == want, "oracle, sigma %g" % sigma
+        buf = (C.c_float * 65)()
+        r = C.c_size_t(0)
+        rc = lib.flow3d_gauss_taps(sigma, buf, 65, C.byref(r))
+        if radius > 32:
+            assert rc == -2  # FLOW3D_ERR_UNSUPPORTED, the kernels' limit
+        else:
+            assert rc == 0 and r.value == radius
+            got = np.frombuffer(buf, np.float32, 2 * radius + 1).view(np.uint32)
+            assert [int(x) for x in got] == want, "library, sigma %g" % sigma
+        n += 1
+    assert n == 15
