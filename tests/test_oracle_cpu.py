@@ -103,3 +103,32 @@ def test_oracle_level_count_equals_the_reference_function(oracle):
             n += 1
             bad += int(oracle.max_warp_level(w, h, d, scale) != want)
     assert n > 10000 and bad == 0
+
+
+def test_warp_agrees_with_the_references_own_cpu_registration(oracle):
+    """Cross-check named in SURVEY.md 8c: the reference carries a CPU version of the backward registration
+    (cuda_operation_register_p.cpp:96-139).  tests/golden/warp_cpu/ holds its output for a small case with random
+    flows plus the special voxels (integer shifts, exact borders, one ulp past the border, NaN, +-inf, -0, 1e9),
+    produced by that code compiled from /root/reference (scripts/make_warp_golden.sh).
+    * the out-of-volume / NaN fallback (out = frame_0) must hit exactly the same voxels;
+    * integer displacements (zero fractions) must agree bit for bit;
+    * elsewhere the CPU loop rounds every product and sum separately while the GPU kernel the oracle mirrors
+      contracts them into FMAs (registration_3d.cu:66-79 as compiled), so the tolerance is 8 ulp of the
+      frames' range (255): 1.3e-4; observed max 6.1e-5, 79 % of the voxels bit-equal."""
+    import json
+    import os
+    from conftest import ROOT
+    g = os.path.join(ROOT, "tests", "golden", "warp_cpu")
+    c = json.load(open(os.path.join(g, "case.json")))
+    W, H, D = c["W"], c["H"], c["D"]
+
+    def ld(name):
+        return np.fromfile(os.path.join(g, name + ".raw"), np.float32).reshape(D, H, W)
+    f0, f1, u, v, w, ref = (ld(n) for n in ("f0", "f1", "u", "v", "w", "warped_ref_cpu"))
+    got = oracle.warp(f0, f1, u, v, w, tuple(c["h"]))
+    assert not np.isnan(got).any() and not np.isnan(ref).any()
+    assert np.array_equal(got == f0, ref == f0)                      # same fallback voxels
+    assert int((got == f0).sum()) == 277
+    assert np.array_equal(got[0, 0], ref[0, 0]) and np.array_equal(got[1, 1], ref[1, 1])  # integer shifts
+    assert np.abs(got - ref).max() <= 1.3e-4
+    assert (got.view(np.uint32) == ref.view(np.uint32)).mean() > 0.7
