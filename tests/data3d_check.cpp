@@ -9,9 +9,10 @@
 
 #include "flow3d/data3d.h"
 
+#define DATA3D_DELETE_AT_END 1
 #include "data3d_ops.inc"
 
 int main(int argc, char** argv) {
   if (argc < 2) return 2;
-  return run_ops(std::string(argv[1]));  // destructors run: a failed read must leave nothing to double-free
+  return run_ops(std::string(argv[1]));  // every volume is deleted at the end: a failed read must leave nothing to double-free
 }
