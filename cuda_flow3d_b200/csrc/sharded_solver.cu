@@ -1058,7 +1058,12 @@ int flow3d_mgpu_compute_host(size_t W, size_t H, size_t D, int n_devices, const 
   }
   const size_t ghost = flow3d_sharded_frame_ghost(W, H, D, n_devices, params, g_group->ranks[0]->min_planes,
                                                   g_group->ranks[0]->min_voxels);
-  if (ghost == 0) return FLOW3D_ERR_INVALID_ARG;
+  if (ghost == 0) {
+    std::fprintf(stderr, "flow3d_mgpu: %zux%zux%zu cannot be z-sharded over %d devices with these parameters (the ghost "
+                 "depth inner_iterations_count + 1 must cover the median's reach: inner >= median_radius / 2 + 1)\n",
+                 W, H, D, n_devices);
+    return FLOW3D_ERR_INVALID_ARG;
+  }
   const size_t ld = flow3d_aligned_ld(W);
   std::vector<float> ms(n_devices, 0.f);
   std::vector<std::thread> th;

@@ -71,7 +71,10 @@ int flow3d_sharded_set_thresholds(flow3d_sharded* s, size_t min_planes_per_rank,
  * frame inside its own frame slab (own planes +- frame_ghost).  FLOW3D_OK, or FLOW3D_ERR_INVALID_ARG with the
  * first offending level / rank (either may be NULL).  flow3d_sharded_compute runs the same check before it
  * touches the device, so an unsupported geometry fails identically on every rank instead of leaving the others
- * inside a collective. */
+ * inside a collective.  What it can refuse: a frame ghost shorter than the coarsest level's source interval
+ * (use flow3d_sharded_frame_ghost), and parameter sets whose ghost depth inner_iterations_count + 1 does not
+ * cover the median's reach plus the prolongation's source margin -- inner_iterations_count >= median_radius / 2 + 1
+ * always passes (the defaults: 5 >= 3). */
 int flow3d_sharded_plan_check(size_t width, size_t height, size_t depth, int world, const flow3d_params* params,
                               size_t min_planes_per_rank, size_t min_voxels_per_rank, size_t frame_ghost,
                               int* bad_level, int* bad_rank);

@@ -97,3 +97,25 @@ def test_frame_ghost_grows_with_the_coarsest_source_interval():
         assert m.frame_ghost(1024, 1024, 1024, world) == 32
         assert m.frame_ghost(256, 256, 256, world, None, 8, 1) == 32
     assert m.frame_ghost(2048, 2048, 2048, 8, {"warp_levels_count": 80}) == 64
+
+
+def test_plan_passes_whenever_the_ghost_depth_covers_the_median():
+    """documented in flow3d_mgpu_c.h: with whole-frame ghosts, inner >= median_radius // 2 + 1 is sufficient for every
+    geometry (sampled); below that the plan check refuses some geometries up front instead of mid-solve"""
+    import random
+    import cuda_flow3d_b200.mgpu as m
+    rnd = random.Random(11)
+    refused_below = 0
+    for _ in range(1500):
+        W, H, D = rnd.randint(8, 300), rnd.randint(8, 300), rnd.randint(40, 2100)
+        world = rnd.choice([2, 3, 4, 8])
+        med = rnd.choice([1, 3, 5, 7])
+        inner = rnd.randint(0, 7)
+        P = {"warp_levels_count": 40, "warp_scale_factor": rnd.choice([0.5, 0.8, 0.95]), "inner_iterations_count": inner,
+             "median_radius": med}
+        ok, lv, rk = m.plan_check(W, H, D, world, P, min_planes=2, min_voxels=1, frame_ghost=D)
+        if inner >= med // 2 + 1:
+            assert ok, (W, H, D, world, P, lv, rk)
+        else:
+            refused_below += int(not ok)
+    assert refused_below > 0
